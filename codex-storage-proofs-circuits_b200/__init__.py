@@ -1,0 +1,16 @@
+"""codex-storage-proofs-circuits_b200 -- B200 (sm_100a) slot-commitment backend for Codex storage proofs.
+
+The package holds only what the hot path needs:
+  csrc/          hand-written CUDA (BN254 Fr, Poseidon2, cell sponge, Merkle levels, path gather) + the C ABI
+  capi.py        ctypes binding of libcodexcommit.so (include/codex_commit.h)
+  proof_input.py host-side mirror of reference/nim/proof_input (same proc names, arguments, error behaviour)
+  build.py       nvcc recipe (in-tree libcodexcommit.so)
+
+The directory name is not a Python identifier; import it with
+    importlib.import_module("codex-storage-proofs-circuits_b200")
+(tests/conftest.py and bench.py do exactly that).
+"""
+from . import capi  # noqa: F401
+from .capi import CodexCommitError, Context, Slot, load_library  # noqa: F401
+
+__all__ = ["capi", "Context", "Slot", "CodexCommitError", "load_library"]

@@ -1,0 +1,781 @@
+// capi.cu -- the C ABI of libcodexcommit.so (include/codex_commit.h) over the sm_100a kernels.
+// No CPU arithmetic lives here: every field operation is a kernel launch; without a CUDA device the context
+// cannot be created and every entry point fails.
+#include "../../include/codex_commit.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace cdx;
+
+// ---------------------------------------------------------------------------------------------------------
+
+struct cdx_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_stream = nullptr;  // H2D staging for *_host entry points
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+  void* d_stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  uint64_t launches = 0;
+  char err[256] = {0};
+};
+
+struct cdx_slot {
+  cdx_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  size_t cell_size = 0, block_size = 0;
+  uint64_t n_local_cells = 0, n_local_blocks = 0, first_block = 0, n_total_blocks = 0;
+  uint32_t cpb_log2 = 0;        // log2(cells per block)
+  uint32_t block_depth = 0;     // path levels inside a block tree (= cpb_log2, or 1 for one-cell blocks)
+  uint32_t slot_depth = 0;      // layers-1 of the slot tree
+  uint32_t top_level = 0;       // levels < top_level are held for the local range only
+  bool has_top = false;
+  uint8_t* d_forest = nullptr;  // block-forest levels 0..block_depth, concatenated
+  uint8_t* d_low = nullptr;     // slot levels 1..top_level (local ranges), concatenated
+  uint8_t* d_top = nullptr;     // slot levels top_level..slot_depth (global), concatenated
+  bool top0_alias = false;      // top level storage for level top_level aliases forest/low (non-sharded case)
+  std::vector<uint8_t*> forest, low, top;             // per-level pointers (low[0] aliases forest[block_depth])
+  std::vector<uint64_t> low_first, low_count, width;  // width[l] = global width of slot level l
+};
+
+static int fail(cdx_ctx* ctx, int status, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+    va_end(ap);
+  }
+  return status;
+}
+
+#define CU_TRY(ctx, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail((ctx), CDX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline unsigned grid_for(size_t n, unsigned block = CDX_BLOCK) { return (unsigned)((n + block - 1) / block); }
+
+#define LAUNCH(ctx, kernel, n_threads, stream, ...)                                    \
+  do {                                                                                 \
+    kernel<<<grid_for(n_threads), CDX_BLOCK, 0, (stream)>>>(__VA_ARGS__);              \
+    (ctx)->launches++;                                                                 \
+    CU_TRY(ctx, cudaGetLastError());                                                   \
+  } while (0)
+
+// ---- context ------------------------------------------------------------------------------------------------
+
+extern "C" int cdx_abi_version(void) { return CDX_ABI_VERSION; }
+
+extern "C" const char* cdx_status_string(int s) {
+  switch (s) {
+    case CDX_OK: return "ok";
+    case CDX_ERR_ARG: return "bad argument";
+    case CDX_ERR_SIZE: return "sizes are not divisible as required";
+    case CDX_ERR_NOT_POW2: return "number of cells must be a power of two";
+    case CDX_ERR_RANGE: return "index or depth out of range";
+    case CDX_ERR_CUDA: return "CUDA error / no device";
+    case CDX_ERR_ALLOC: return "allocation failed";
+    case CDX_ERR_STATE: return "handle is not in the required state";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
+  if (!out) return CDX_ERR_ARG;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) return CDX_ERR_CUDA;
+  cdx_ctx* ctx = new (std::nothrow) cdx_ctx();
+  if (!ctx) return CDX_ERR_ALLOC;
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    delete ctx;
+    return CDX_ERR_CUDA;
+  }
+  *out = ctx;
+  return CDX_OK;
+}
+
+extern "C" void cdx_ctx_destroy(cdx_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+  }
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+extern "C" const char* cdx_last_error(const cdx_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" uint64_t cdx_launch_count(const cdx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* cdx_ctx_stream(const cdx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// scoped device buffer for the *_host entry points
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  uint8_t* u8() const { return static_cast<uint8_t*>(p); }
+};
+
+// ---- hash layer ---------------------------------------------------------------------------------------------
+
+extern "C" int cdx_permutation_batch_dev(cdx_ctx* ctx, const void* d_in, void* d_out, size_t n, void* stream) {
+  if (!ctx || !d_in || !d_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (n == 0) return CDX_OK;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  LAUNCH(ctx, k_permutation_batch, n, st, (const uint8_t*)d_in, (uint8_t*)d_out, n);
+  return CDX_OK;
+}
+
+extern "C" int cdx_permutation_batch_host(cdx_ctx* ctx, const uint8_t* in, uint8_t* out, size_t n) {
+  if (!ctx || !in || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (n == 0) return CDX_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf di, dout;
+  CU_TRY(ctx, di.alloc(96 * n));
+  CU_TRY(ctx, dout.alloc(96 * n));
+  CU_TRY(ctx, cudaMemcpyAsync(di.p, in, 96 * n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = cdx_permutation_batch_dev(ctx, di.p, dout.p, n, ctx->stream);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(out, dout.p, 96 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_sponge_felts_batch_host(cdx_ctx* ctx, const uint8_t* elems, size_t n_items, size_t len, int rate, uint8_t* out) {
+  if (!ctx || !out || (!elems && len)) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (rate != 1 && rate != 2) return fail(ctx, CDX_ERR_ARG, "rate must be 1 or 2");
+  if (len > 0xffffffffu / 32) return fail(ctx, CDX_ERR_SIZE, "sponge input too long");
+  if (n_items == 0) return CDX_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf di, dout;
+  CU_TRY(ctx, di.alloc(32 * len * n_items));
+  CU_TRY(ctx, dout.alloc(32 * n_items));
+  if (len) CU_TRY(ctx, cudaMemcpyAsync(di.p, elems, 32 * len * n_items, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_sponge_felts, n_items, ctx->stream, di.u8(), n_items, (uint32_t)len, rate, dout.u8());
+  CU_TRY(ctx, cudaMemcpyAsync(out, dout.p, 32 * n_items, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_hash_bytes_batch_host(cdx_ctx* ctx, const uint8_t* data, size_t n_items, size_t len, uint8_t* out) {
+  if (!ctx || !out || (!data && len)) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (len > 0x7fffffffu) return fail(ctx, CDX_ERR_SIZE, "byte string too long");
+  if (n_items == 0) return CDX_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf di, dout;
+  CU_TRY(ctx, di.alloc(len * n_items));
+  CU_TRY(ctx, dout.alloc(32 * n_items));
+  if (len) CU_TRY(ctx, cudaMemcpyAsync(di.p, data, len * n_items, cudaMemcpyHostToDevice, ctx->stream));
+  if (len % 4 == 0 && len > 0)   // cudaMalloc'd base is 256-byte aligned, so every item is word aligned
+    LAUNCH(ctx, k_hash_cells, n_items, ctx->stream, (const uint32_t*)di.p, n_items, (uint32_t)(len / 4), dout.u8());
+  else
+    LAUNCH(ctx, k_hash_bytes_any, n_items, ctx->stream, di.u8(), n_items, (uint32_t)len, dout.u8());
+  CU_TRY(ctx, cudaMemcpyAsync(out, dout.p, 32 * n_items, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_compress_batch_host(cdx_ctx* ctx, const uint8_t* x, const uint8_t* y, const uint32_t* keys, size_t n, uint8_t* out) {
+  if (!ctx || !x || !y || !keys || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  for (size_t i = 0; i < n; ++i)
+    if (keys[i] > 3) return fail(ctx, CDX_ERR_ARG, "key %u at %zu is not in 0..3", keys[i], i);
+  if (n == 0) return CDX_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf dx, dy, dk, dout;
+  CU_TRY(ctx, dx.alloc(32 * n));
+  CU_TRY(ctx, dy.alloc(32 * n));
+  CU_TRY(ctx, dk.alloc(4 * n));
+  CU_TRY(ctx, dout.alloc(32 * n));
+  CU_TRY(ctx, cudaMemcpyAsync(dx.p, x, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(dy.p, y, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(dk.p, keys, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_compress_batch, n, ctx->stream, dx.u8(), dy.u8(), (const uint32_t*)dk.p, n, dout.u8());
+  CU_TRY(ctx, cudaMemcpyAsync(out, dout.p, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+// ---- Merkle trees -------------------------------------------------------------------------------------------
+
+extern "C" size_t cdx_merkle_total_nodes(size_t n, int bottom_layer) {
+  if (n == 0) return 0;
+  size_t total = 0;
+  bool bottom = bottom_layer != 0;
+  for (;;) {
+    total += n;
+    if (!bottom && n == 1) return total;
+    n = (n + 1) / 2;
+    bottom = false;
+  }
+}
+
+extern "C" int cdx_merkle_num_layers(size_t n, int bottom_layer) {
+  if (n == 0) return 0;
+  int layers = 1;
+  bool bottom = bottom_layer != 0;
+  for (;;) {
+    if (!bottom && n == 1) return layers;
+    n = (n + 1) / 2;
+    bottom = false;
+    ++layers;
+  }
+}
+
+// builds every level above d_layers[0..n) in place (layers concatenated); level kernels run back to back on st
+static int merkle_layers_on_device(cdx_ctx* ctx, uint8_t* d_layers, size_t n, bool bottom, cudaStream_t st) {
+  uint8_t* cur = d_layers;
+  for (;;) {
+    if (!bottom && n == 1) return CDX_OK;
+    uint8_t* next = cur + 32 * n;
+    LAUNCH(ctx, k_merkle_level, (n + 1) / 2, st, cur, n, next, bottom ? 1u : 0u, 0);
+    cur = next;
+    n = (n + 1) / 2;
+    bottom = false;
+  }
+}
+
+extern "C" int cdx_merkle_layers_host(cdx_ctx* ctx, const uint8_t* leaves, size_t n, int bottom_layer, uint8_t* layers_out) {
+  if (!ctx || !leaves || !layers_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (n == 0) return fail(ctx, CDX_ERR_ARG, "merkle tree of empty input");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t total = cdx_merkle_total_nodes(n, bottom_layer);
+  DevBuf d;
+  CU_TRY(ctx, d.alloc(32 * total));
+  CU_TRY(ctx, cudaMemcpyAsync(d.p, leaves, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = merkle_layers_on_device(ctx, d.u8(), n, bottom_layer != 0, ctx->stream);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(layers_out, d.p, 32 * total, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_merkle_root_host(cdx_ctx* ctx, const uint8_t* leaves, size_t n, uint8_t root_out[32]) {
+  if (!ctx || !leaves || !root_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (n == 0) return fail(ctx, CDX_ERR_ARG, "merkle tree of empty input");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t total = cdx_merkle_total_nodes(n, 1);
+  DevBuf d;
+  CU_TRY(ctx, d.alloc(32 * total));
+  CU_TRY(ctx, cudaMemcpyAsync(d.p, leaves, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = merkle_layers_on_device(ctx, d.u8(), n, true, ctx->stream);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(root_out, d.u8() + 32 * (total - 1), 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+// ---- slot commitment ----------------------------------------------------------------------------------------
+
+static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+static uint32_t log2_u64(uint64_t x) {
+  uint32_t k = 0;
+  while ((1ull << k) < x) ++k;
+  return k;
+}
+
+extern "C" void cdx_slot_free(cdx_slot* s) {
+  if (!s) return;
+  if (s->ctx) cudaSetDevice(s->ctx->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->d_forest) cudaFree(s->d_forest);
+  if (s->d_low) cudaFree(s->d_low);
+  if (s->d_top) cudaFree(s->d_top);
+  delete s;
+}
+
+static int check_shape(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t block_size) {
+  if (cell_size == 0 || cell_size % 4 || cell_size > (1u << 30)) return fail(ctx, CDX_ERR_SIZE, "cell size %zu must be a non-zero multiple of 4", cell_size);
+  if (block_size == 0 || block_size % cell_size) return fail(ctx, CDX_ERR_SIZE, "block size is not divisible by cell size");
+  if (!is_pow2(block_size / cell_size)) return fail(ctx, CDX_ERR_SIZE, "cells per block (%zu) must be a power of two", block_size / cell_size);
+  if (n_bytes == 0 || n_bytes % block_size) return fail(ctx, CDX_ERR_SIZE, "slot size %zu is not a non-zero multiple of the block size", n_bytes);
+  return CDX_OK;
+}
+
+// allocate a slot handle and lay out its layers; on success the caller fills forest[0] and calls build_trees
+static int slot_alloc(cdx_ctx* ctx, uint64_t n_local_blocks, size_t cell_size, size_t block_size, uint64_t first_block,
+                      uint64_t n_total_blocks, int top_level, cudaStream_t st, cdx_slot** out) {
+  const uint64_t cpb = block_size / cell_size;
+  if (n_total_blocks == 0 || n_local_blocks == 0 || first_block + n_local_blocks > n_total_blocks)
+    return fail(ctx, CDX_ERR_RANGE, "block range [%llu,+%llu) outside slot of %llu blocks", (unsigned long long)first_block,
+                (unsigned long long)n_local_blocks, (unsigned long long)n_total_blocks);
+  cdx_slot* s = new (std::nothrow) cdx_slot();
+  if (!s) return fail(ctx, CDX_ERR_ALLOC, "host allocation failed");
+  s->ctx = ctx;
+  s->stream = st;
+  s->cell_size = cell_size;
+  s->block_size = block_size;
+  s->n_local_blocks = n_local_blocks;
+  s->n_local_cells = n_local_blocks * cpb;
+  s->first_block = first_block;
+  s->n_total_blocks = n_total_blocks;
+  s->cpb_log2 = log2_u64(cpb);
+  s->block_depth = cpb == 1 ? 1 : s->cpb_log2;
+  // global widths of the slot tree (merkle/bn254.nim:29-60): n, ceil(n/2), ..., 1; a single block still gets
+  // one key-3 compression
+  {
+    uint64_t w = n_total_blocks;
+    bool bottom = true;
+    for (;;) {
+      s->width.push_back(w);
+      if (!bottom && w == 1) break;
+      w = (w + 1) / 2;
+      bottom = false;
+    }
+    s->slot_depth = (uint32_t)s->width.size() - 1;
+  }
+  if (top_level < 0 || (uint32_t)top_level > s->slot_depth || (n_total_blocks == 1 && top_level != 0)) {
+    delete s;
+    return fail(ctx, CDX_ERR_RANGE, "top_level %d outside 0..%u", top_level, s->slot_depth);
+  }
+  s->top_level = (uint32_t)top_level;
+  const uint64_t align = 1ull << top_level;
+  if (first_block % align || (n_local_blocks % align && first_block + n_local_blocks != n_total_blocks)) {
+    delete s;
+    return fail(ctx, CDX_ERR_SIZE, "block range is not aligned to 2^top_level");
+  }
+  // forest: levels 0..block_depth
+  size_t forest_nodes = 0;
+  std::vector<size_t> f_off;
+  for (uint32_t l = 0; l <= s->block_depth; ++l) {
+    f_off.push_back(forest_nodes);
+    forest_nodes += cpb == 1 ? s->n_local_cells : (s->n_local_cells >> l);
+  }
+  // low: slot levels 1..top_level over the local range
+  size_t low_nodes = 0;
+  std::vector<size_t> l_off;
+  s->low_first.assign(s->top_level + 1, 0);
+  s->low_count.assign(s->top_level + 1, 0);
+  s->low_first[0] = first_block;
+  s->low_count[0] = n_local_blocks;
+  l_off.push_back(0);
+  for (uint32_t l = 1; l <= s->top_level; ++l) {
+    s->low_first[l] = first_block >> l;
+    s->low_count[l] = (s->low_count[l - 1] + 1) / 2;
+    l_off.push_back(low_nodes);
+    low_nodes += s->low_count[l];
+  }
+  cudaError_t e = cudaMalloc((void**)&s->d_forest, 32 * forest_nodes);
+  if (e == cudaSuccess && low_nodes) e = cudaMalloc((void**)&s->d_low, 32 * low_nodes);
+  if (e != cudaSuccess) {
+    cdx_slot_free(s);
+    return fail(ctx, CDX_ERR_ALLOC, "cudaMalloc of %zu tree nodes failed: %s", forest_nodes + low_nodes, cudaGetErrorString(e));
+  }
+  for (uint32_t l = 0; l <= s->block_depth; ++l) s->forest.push_back(s->d_forest + 32 * f_off[l]);
+  s->low.push_back(s->forest[s->block_depth]);
+  for (uint32_t l = 1; l <= s->top_level; ++l) s->low.push_back(s->d_low + 32 * l_off[l]);
+  *out = s;
+  return CDX_OK;
+}
+
+// block forest + local slot levels, assuming forest[0] (cell hashes) is already being produced on s->stream
+static int build_local_trees(cdx_slot* s) {
+  cdx_ctx* ctx = s->ctx;
+  const bool singles = (s->block_size / s->cell_size) == 1;
+  if (singles) {
+    LAUNCH(ctx, k_merkle_level, s->n_local_cells, s->stream, s->forest[0], (size_t)s->n_local_cells, s->forest[1], 1u, 1);
+  } else {
+    for (uint32_t l = 0; l < s->block_depth; ++l) {
+      const size_t n = s->n_local_cells >> l;
+      LAUNCH(ctx, k_merkle_level, n / 2, s->stream, s->forest[l], n, s->forest[l + 1], l == 0 ? 1u : 0u, 0);
+    }
+  }
+  for (uint32_t l = 0; l < s->top_level; ++l) {
+    const size_t n = s->low_count[l];
+    LAUNCH(ctx, k_merkle_level, (n + 1) / 2, s->stream, s->low[l], n, s->low[l + 1], l == 0 ? 1u : 0u, 0);
+  }
+  return CDX_OK;
+}
+
+// upper (replicated) levels from the complete level-top_level layer
+static int build_top(cdx_slot* s, const uint8_t* d_level_nodes, bool alias) {
+  cdx_ctx* ctx = s->ctx;
+  const uint32_t T = s->top_level;
+  size_t nodes = 0;
+  std::vector<size_t> off;
+  for (uint32_t l = T; l <= s->slot_depth; ++l) {
+    off.push_back(nodes);
+    if (!(alias && l == T)) nodes += s->width[l];
+  }
+  if (s->d_top) {
+    cudaFree(s->d_top);
+    s->d_top = nullptr;
+  }
+  if (nodes) CU_TRY(ctx, cudaMalloc((void**)&s->d_top, 32 * nodes));
+  s->top.assign(s->slot_depth + 1, nullptr);
+  for (uint32_t l = T; l <= s->slot_depth; ++l) s->top[l] = s->d_top + 32 * off[l - T];
+  if (alias) {
+    s->top[T] = const_cast<uint8_t*>(d_level_nodes);
+  } else {
+    CU_TRY(ctx, cudaMemcpyAsync(s->top[T], d_level_nodes, 32 * s->width[T], cudaMemcpyDeviceToDevice, s->stream));
+  }
+  s->top0_alias = alias;
+  for (uint32_t l = T; l < s->slot_depth; ++l) {
+    const size_t n = s->width[l];
+    LAUNCH(ctx, k_merkle_level, (n + 1) / 2, s->stream, s->top[l], n, s->top[l + 1], l == 0 ? 1u : 0u, 0);
+  }
+  s->has_top = true;
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_commit_range_dev(cdx_ctx* ctx, const void* d_data, size_t n_local_bytes, size_t cell_size, size_t block_size,
+                                         uint64_t first_block, uint64_t n_total_blocks, int top_level, void* stream, cdx_slot** out) {
+  if (!ctx || !d_data || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  *out = nullptr;
+  int rc = check_shape(ctx, n_local_bytes, cell_size, block_size);
+  if (rc) return rc;
+  if ((uintptr_t)d_data % 16) return fail(ctx, CDX_ERR_ARG, "slot data must be 16-byte aligned");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cdx_slot* s = nullptr;
+  rc = slot_alloc(ctx, n_local_bytes / block_size, cell_size, block_size, first_block, n_total_blocks, top_level, st, &s);
+  if (rc) return rc;
+  auto body = [&]() -> int {
+    LAUNCH(ctx, k_hash_cells, s->n_local_cells, st, (const uint32_t*)d_data, (size_t)s->n_local_cells, (uint32_t)(cell_size / 4), s->forest[0]);
+    return build_local_trees(s);
+  };
+  rc = body();
+  if (rc) {
+    cdx_slot_free(s);
+    return rc;
+  }
+  *out = s;
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_commit_dev(cdx_ctx* ctx, const void* d_data, size_t n_bytes, size_t cell_size, size_t block_size, void* stream, cdx_slot** out) {
+  if (!ctx || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (block_size == 0) return fail(ctx, CDX_ERR_SIZE, "block size is zero");
+  cdx_slot* s = nullptr;
+  int rc = cdx_slot_commit_range_dev(ctx, d_data, n_bytes, cell_size, block_size, 0, n_bytes / block_size, 0, stream, &s);
+  if (rc) return rc;
+  rc = build_top(s, s->low[0], true);
+  if (rc) {
+    cdx_slot_free(s);
+    return rc;
+  }
+  *out = s;
+  return CDX_OK;
+}
+
+static int ensure_stage(cdx_ctx* ctx, size_t bytes) {
+  if (ctx->stage_bytes >= bytes) return CDX_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    ctx->d_stage[i] = nullptr;
+  }
+  ctx->stage_bytes = 0;
+  for (int i = 0; i < 2; ++i) CU_TRY(ctx, cudaMalloc(&ctx->d_stage[i], bytes));
+  ctx->stage_bytes = bytes;
+  return CDX_OK;
+}
+
+// Host-resident slot: the bytes stream through two device tiles; the copy of tile t+1 (copy stream) overlaps the
+// cell sponge of tile t (compute stream).  Only hashes stay resident.
+extern "C" int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
+  if (!ctx || !data || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  *out = nullptr;
+  int rc = check_shape(ctx, n_bytes, cell_size, block_size);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n_blocks = n_bytes / block_size;
+  size_t tile_blocks = ((size_t)64 << 20) / block_size;        // 64 MiB tiles
+  if (tile_blocks == 0) tile_blocks = 1;
+  if (tile_blocks > n_blocks) tile_blocks = n_blocks;
+  const size_t tile_bytes = tile_blocks * block_size;
+  rc = ensure_stage(ctx, tile_bytes);
+  if (rc) return rc;
+  cdx_slot* s = nullptr;
+  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, 0, n_blocks, 0, ctx->stream, &s);
+  if (rc) return rc;
+  const size_t cpb = block_size / cell_size;
+  auto body = [&]() -> int {
+    size_t done = 0;
+    for (int t = 0; done < n_blocks; ++t) {
+      const int b = t & 1;
+      const size_t nb = n_blocks - done < tile_blocks ? n_blocks - done : tile_blocks;
+      if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+      CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+      CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+      LAUNCH(ctx, k_hash_cells, nb * cpb, ctx->stream, (const uint32_t*)ctx->d_stage[b], nb * cpb, (uint32_t)(cell_size / 4),
+             s->forest[0] + 32 * done * cpb);
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+      done += nb;
+    }
+    int r = build_local_trees(s);
+    if (r) return r;
+    r = build_top(s, s->low[0], true);
+    if (r) return r;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDX_OK;
+  };
+  rc = body();
+  if (rc) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    cdx_slot_free(s);
+    return rc;
+  }
+  *out = s;
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells, size_t cell_size, size_t block_size, cdx_slot** out) {
+  if (!ctx || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  *out = nullptr;
+  if (cell_size == 0 || n_cells == 0 || n_cells > ((size_t)1 << 40) / cell_size) return fail(ctx, CDX_ERR_SIZE, "bad fake slot size");
+  int rc = check_shape(ctx, n_cells * cell_size, cell_size, block_size);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf d;
+  CU_TRY(ctx, d.alloc(n_cells * cell_size));
+  rc = cdx_fake_cells_dev(ctx, seed, 0, n_cells, cell_size, d.p, ctx->stream);
+  if (rc) return rc;
+  cdx_slot* s = nullptr;
+  rc = cdx_slot_commit_dev(ctx, d.p, n_cells * cell_size, cell_size, block_size, ctx->stream, &s);
+  if (rc) return rc;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);   // the data buffer dies with this scope
+  if (e != cudaSuccess) {
+    cdx_slot_free(s);
+    return fail(ctx, CDX_ERR_CUDA, "fake slot commit failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_subtree_root_count(const cdx_slot* s, uint64_t* first_node, uint64_t* n_nodes) {
+  if (!s) return CDX_ERR_ARG;
+  if (first_node) *first_node = s->low_first[s->top_level];
+  if (n_nodes) *n_nodes = s->low_count[s->top_level];
+  return CDX_OK;
+}
+
+extern "C" const void* cdx_slot_subtree_roots_dev(const cdx_slot* s) { return s ? s->low[s->top_level] : nullptr; }
+
+extern "C" int cdx_slot_set_top_dev(cdx_slot* s, const void* d_level_nodes, uint64_t n_level_nodes, void* stream) {
+  if (!s || !d_level_nodes) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  if (n_level_nodes != s->width[s->top_level])
+    return fail(ctx, CDX_ERR_SIZE, "expected %llu level-%u nodes, got %llu", (unsigned long long)s->width[s->top_level], s->top_level,
+                (unsigned long long)n_level_nodes);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (stream && (cudaStream_t)stream != s->stream) {   // order after everything queued on the old stream
+    CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+    s->stream = (cudaStream_t)stream;
+  }
+  return build_top(s, (const uint8_t*)d_level_nodes, false);
+}
+
+extern "C" int cdx_slot_root(const cdx_slot* s, uint8_t root_out[32]) {
+  if (!s || !root_out) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "sharded slot has no top tree yet (call cdx_slot_set_top_dev)");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaMemcpyAsync(root_out, s->top[s->slot_depth], 32, cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_shape(const cdx_slot* s, uint64_t* n_cells, uint64_t* n_blocks, uint32_t* block_tree_depth, uint32_t* slot_tree_depth) {
+  if (!s) return CDX_ERR_ARG;
+  if (n_cells) *n_cells = s->n_total_blocks * (s->block_size / s->cell_size);
+  if (n_blocks) *n_blocks = s->n_total_blocks;
+  if (block_tree_depth) *block_tree_depth = s->block_depth;
+  if (slot_tree_depth) *slot_tree_depth = s->slot_depth;
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_read_layer(const cdx_slot* s, int tree, uint32_t level, uint64_t first, uint64_t count, uint8_t* out) {
+  if (!s || !out) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  if (count == 0) return CDX_OK;
+  const uint8_t* src = nullptr;
+  if (tree == 0) {
+    if (level > s->block_depth) return fail(ctx, CDX_ERR_RANGE, "block-forest level %u > %u", level, s->block_depth);
+    const uint64_t cpb = s->block_size / s->cell_size;
+    const uint64_t per_block = cpb == 1 ? 1 : (cpb >> level);
+    const uint64_t lo = s->first_block * per_block, n = s->n_local_blocks * per_block;
+    if (first < lo || first + count > lo + n) return fail(ctx, CDX_ERR_RANGE, "nodes [%llu,+%llu) not held locally", (unsigned long long)first, (unsigned long long)count);
+    src = s->forest[level] + 32 * (first - lo);
+  } else if (tree == 1) {
+    if (level > s->slot_depth) return fail(ctx, CDX_ERR_RANGE, "slot-tree level %u > %u", level, s->slot_depth);
+    if (level >= s->top_level) {
+      if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "no top tree yet");
+      if (first + count > s->width[level]) return fail(ctx, CDX_ERR_RANGE, "nodes out of range");
+      src = s->top[level] + 32 * first;
+    } else {
+      if (first < s->low_first[level] || first + count > s->low_first[level] + s->low_count[level])
+        return fail(ctx, CDX_ERR_RANGE, "nodes not held locally");
+      src = s->low[level] + 32 * (first - s->low_first[level]);
+    }
+  } else {
+    return fail(ctx, CDX_ERR_ARG, "tree must be 0 (block forest) or 1 (slot tree)");
+  }
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaMemcpyAsync(out, src, 32 * count, cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indices, size_t n_samples, size_t max_depth, uint8_t* out, uint8_t* leaf_out) {
+  if (!s || !cell_indices || !out) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "no top tree yet");
+  if (n_samples == 0) return CDX_OK;
+  const uint64_t n_cells_total = s->n_total_blocks << s->cpb_log2;
+  if (max_depth < s->block_depth + s->slot_depth || max_depth > 64)
+    return fail(ctx, CDX_ERR_RANGE, "max_depth %zu < path length %u (padMerkleProof)", max_depth, s->block_depth + s->slot_depth);
+  if (n_samples > (1u << 20)) return fail(ctx, CDX_ERR_SIZE, "too many samples in one call");
+  for (size_t i = 0; i < n_samples; ++i)
+    if (cell_indices[i] >= n_cells_total) return fail(ctx, CDX_ERR_RANGE, "cell index %llu >= %llu", (unsigned long long)cell_indices[i], (unsigned long long)n_cells_total);
+  if (s->block_depth > 32 || s->slot_depth >= 40) return fail(ctx, CDX_ERR_RANGE, "tree too deep for the path plan");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  PathPlan plan;
+  memset(&plan, 0, sizeof plan);
+  plan.singles = (s->block_size / s->cell_size) == 1 ? 1u : 0u;
+  for (uint32_t l = 0; l < s->block_depth; ++l) plan.forest[l] = s->forest[l];
+  for (uint32_t l = 0; l <= s->slot_depth; ++l) {
+    plan.width[l] = s->width[l];
+    if (l >= s->top_level) plan.top[l] = s->top[l];
+    else {
+      plan.low[l] = s->low[l];
+      plan.low_first[l] = s->low_first[l];
+      plan.low_count[l] = s->low_count[l];
+    }
+  }
+  plan.first_cell = s->first_block << s->cpb_log2;
+  plan.n_local_cells = s->n_local_cells;
+  plan.block_depth = s->block_depth;
+  plan.slot_depth = s->slot_depth;
+  plan.top_level = s->top_level;
+  plan.cells_per_block_log2 = s->cpb_log2;
+  DevBuf d_idx, d_out, d_leaf;
+  CU_TRY(ctx, d_idx.alloc(8 * n_samples));
+  CU_TRY(ctx, d_out.alloc(32 * n_samples * max_depth));
+  CU_TRY(ctx, d_leaf.alloc(32 * n_samples));
+  CU_TRY(ctx, cudaMemcpyAsync(d_idx.p, cell_indices, 8 * n_samples, cudaMemcpyHostToDevice, s->stream));
+  const size_t threads = n_samples * (max_depth + 1) * 2;
+  k_gather_paths<<<grid_for(threads, 256), 256, 0, s->stream>>>(plan, (const uint64_t*)d_idx.p, (uint32_t)n_samples, (uint32_t)max_depth,
+                                                               d_out.u8(), d_leaf.u8());
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, 32 * n_samples * max_depth, cudaMemcpyDeviceToHost, s->stream));
+  if (leaf_out) CU_TRY(ctx, cudaMemcpyAsync(leaf_out, d_leaf.p, 32 * n_samples, cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+  return CDX_OK;
+}
+
+// ---- sampling and data source -------------------------------------------------------------------------------
+
+extern "C" int cdx_cell_indices(cdx_ctx* ctx, const uint8_t entropy[32], const uint8_t slot_root[32], uint64_t n_cells, size_t n_samples, uint64_t* indices) {
+  if (!ctx || !entropy || !slot_root || !indices) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (!is_pow2(n_cells)) return fail(ctx, CDX_ERR_NOT_POW2, "for this version, `numberOfCells` is assumed to be a power of two");
+  if (n_samples == 0) return CDX_OK;
+  if (n_samples > 0xffffffffu) return fail(ctx, CDX_ERR_SIZE, "too many samples");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf d_in, d_out;
+  CU_TRY(ctx, d_in.alloc(64));
+  CU_TRY(ctx, d_out.alloc(8 * n_samples));
+  CU_TRY(ctx, cudaMemcpyAsync(d_in.p, entropy, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(d_in.u8() + 32, slot_root, 32, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_cell_indices, n_samples, ctx->stream, d_in.u8(), n_cells - 1, (uint32_t)n_samples, (uint64_t*)d_out.p);
+  CU_TRY(ctx, cudaMemcpyAsync(indices, d_out.p, 8 * n_samples, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_fake_cells_dev(cdx_ctx* ctx, uint64_t seed, uint64_t first_cell, size_t n_cells, size_t cell_size, void* d_out, void* stream) {
+  if (!ctx || !d_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (cell_size == 0 || cell_size % 4 || cell_size > (1u << 30)) return fail(ctx, CDX_ERR_SIZE, "cell size must be a non-zero multiple of 4");
+  if (n_cells == 0) return CDX_OK;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  LAUNCH(ctx, k_fake_cells, n_cells, st, seed, first_cell, n_cells, (uint32_t)cell_size, (uint8_t*)d_out);
+  return CDX_OK;
+}
+
+extern "C" int cdx_fake_cells_host(cdx_ctx* ctx, uint64_t seed, uint64_t first_cell, size_t n_cells, size_t cell_size, uint8_t* out) {
+  if (!ctx || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (n_cells == 0) return CDX_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf d;
+  CU_TRY(ctx, d.alloc(n_cells * cell_size));
+  int rc = cdx_fake_cells_dev(ctx, seed, first_cell, n_cells, cell_size, d.p, ctx->stream);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(out, d.p, n_cells * cell_size, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_fill_synthetic_dev(cdx_ctx* ctx, uint64_t seed, uint64_t first_word, size_t n_bytes, void* d_out, void* stream) {
+  if (!ctx || !d_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (n_bytes % 8) return fail(ctx, CDX_ERR_SIZE, "synthetic fill needs a multiple of 8 bytes");
+  if (n_bytes == 0) return CDX_OK;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const size_t n_words = n_bytes / 8;
+  size_t blocks = (n_words + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  k_fill_synthetic<<<(unsigned)blocks, 256, 0, st>>>(seed, first_word, n_words, (uint64_t*)d_out);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return CDX_OK;
+}
+
+// ---- measurement --------------------------------------------------------------------------------------------
+
+extern "C" int cdx_probe_imad_rate(cdx_ctx* ctx, int kind, double* ops_per_second, double* elapsed_ms) {
+  if (!ctx || !ops_per_second) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (kind < 0 || kind > 2) return fail(ctx, CDX_ERR_ARG, "kind must be 0, 1 or 2");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf sink;
+  CU_TRY(ctx, sink.alloc(4));
+  const unsigned blocks = (unsigned)ctx->sm_count * 8, threads = 256;
+  const uint32_t iters = 8192;
+  cudaEvent_t e0, e1;
+  CU_TRY(ctx, cudaEventCreate(&e0));
+  CU_TRY(ctx, cudaEventCreate(&e1));
+  float best = 0.f;
+  for (int rep = 0; rep < 4; ++rep) {   // rep 0 is the warm-up
+    CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    k_probe_imad<<<blocks, threads, 0, ctx->stream>>>(kind, iters, 12345u + rep, (uint32_t*)sink.p);
+    ctx->launches++;
+    CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double ops = (double)blocks * threads * iters * CDX_PROBE_OPS_PER_ITER;
+  *ops_per_second = ops / (best * 1e-3);
+  if (elapsed_ms) *elapsed_ms = best;
+  return CDX_OK;
+}

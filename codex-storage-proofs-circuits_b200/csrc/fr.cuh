@@ -1,0 +1,241 @@
+// fr.cuh -- BN254 scalar field Fr on sm_100a: 8 x 32-bit limbs, Montgomery form (R = 2^256).
+//
+// This is layer L0 of the hot path: the reference gets this arithmetic from third-party
+// packages (constantine for Nim, `proof_input.nimble:11`; zikkurat-algebra for Haskell,
+// `storage-proof-ref.cabal:34`) -- call sites `types/bn254.nim:27,30,58`, `merkle/bn254.nim:24-27`.
+//
+// Multiplication is word-serial Montgomery (CIOS) arranged so that every 32x32->64 product is ONE
+// IMAD.WIDE.U32(.X) with the carry chain riding on the predicate carry: products of even limbs accumulate in
+// an "even" 256-bit accumulator (64-bit slots at limb positions 0,2,4,6) and products of odd limbs in an "odd"
+// one (slots at 1,3,5,7); dividing by 2^32 after each row swaps their roles, so no product ever has to be
+// re-aligned.  Cost per product: 128 IMAD.WIDE.U32 + 8 IMAD (the 2n^2+n of BASELINE.md section 2) and ~30
+// IADD3 on the ALU pipe.
+//
+// Range discipline ("units of r", r < 2^254 so 2^256 > 5.29 r):
+//   mont_mul(a,b) needs a < 4.29 r (= 2^256 - r: the running row sum is < a + r and must fit 256 bits),
+//   a*b < 22 r^2, b anything < 2^256; it returns < (a*b/(5.29 r^2) + 1) r  -- no final subtraction inside.
+//   In particular inputs < 2r give outputs < 2r; inputs < r give outputs < 1.19 r.
+//   add_mod / dbl_mod take inputs < r and return < r.  reduce_once maps [0,2r) -> [0,r).
+//
+// The four carry-chain primitives below are inline PTX.  Compiling this header with a host compiler is only
+// possible with -DCDX_HOST_EMUL, which pulls C emulations of exactly those primitives from
+// tests/host_emul/fr_rows_host.h so that the limb-level logic ABOVE them (reductions, Poseidon2 schedule, byte
+// chunking) can be unit-tested without a GPU.  The product library is always compiled by nvcc for sm_100a and
+// contains no host arithmetic.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CDX_HD __host__ __device__ __forceinline__
+#define CDX_D __device__ __forceinline__
+#else
+#define CDX_HD inline
+#define CDX_D inline
+#endif
+
+namespace cdx {
+
+struct Fr {
+  uint32_t l[8];
+};
+
+// r = 21888242871839275222246405745257275088548364400416034343698204186575808495617 (reference README.md:76)
+#define CDX_N0 0xf0000001u
+#define CDX_N1 0x43e1f593u
+#define CDX_N2 0x79b97091u
+#define CDX_N3 0x2833e848u
+#define CDX_N4 0x8181585du
+#define CDX_N5 0xb85045b6u
+#define CDX_N6 0xe131a029u
+#define CDX_N7 0x30644e72u
+#define CDX_NP 0xefffffffu  // -r^-1 mod 2^32
+
+// R^2 mod r = 2^512 mod r : multiplying by it enters Montgomery form
+#define CDX_R2_INIT {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}
+// R mod r = Montgomery form of 1
+#define CDX_ONE_INIT {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}
+
+#if defined(__CUDA_ARCH__)
+// ---------------------------------------------------------------------------------------------------------
+// carry-chain primitives, sm_100a PTX.  Each asm statement is self-contained with respect to the carry flag.
+
+// e/o <- products of the even/odd limbs of a with bi (first row: accumulators start empty)
+CDX_D void mont_row_first(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
+  asm("{\n\t"
+      ".reg .u64 t;\n\t"
+      "mul.wide.u32 t, %16, %24; mov.b64 {%0, %1}, t;\n\t"
+      "mul.wide.u32 t, %18, %24; mov.b64 {%2, %3}, t;\n\t"
+      "mul.wide.u32 t, %20, %24; mov.b64 {%4, %5}, t;\n\t"
+      "mul.wide.u32 t, %22, %24; mov.b64 {%6, %7}, t;\n\t"
+      "mul.wide.u32 t, %17, %24; mov.b64 {%8, %9}, t;\n\t"
+      "mul.wide.u32 t, %19, %24; mov.b64 {%10, %11}, t;\n\t"
+      "mul.wide.u32 t, %21, %24; mov.b64 {%12, %13}, t;\n\t"
+      "mul.wide.u32 t, %23, %24; mov.b64 {%14, %15}, t;\n\t"
+      "}"
+      : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7]),
+        "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(bi));
+}
+
+// Next row.  On entry e is the even-aligned accumulator (limb positions 0..7) and o is the previous row's even
+// accumulator after the divide by 2^32 (o[k] sits at position k-1, o[0] is dead).  On exit e holds positions
+// 0..7 and o positions 1..8 of  T + a*bi.
+CDX_D void mont_row_next(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %8, %17, %24, %10;  madc.hi.cc.u32 %9, %17, %24, %11;\n\t"
+      "madc.lo.cc.u32 %10, %19, %24, %12; madc.hi.cc.u32 %11, %19, %24, %13;\n\t"
+      "madc.lo.cc.u32 %12, %21, %24, %14; madc.hi.cc.u32 %13, %21, %24, %15;\n\t"
+      "madc.lo.cc.u32 %14, %23, %24, 0;   madc.hi.u32 %15, %23, %24, 0;\n\t"
+      "mad.lo.cc.u32 %0, %16, %24, %0;  madc.hi.cc.u32 %1, %16, %24, %1;\n\t"
+      "madc.lo.cc.u32 %2, %18, %24, %2; madc.hi.cc.u32 %3, %18, %24, %3;\n\t"
+      "madc.lo.cc.u32 %4, %20, %24, %4; madc.hi.cc.u32 %5, %20, %24, %5;\n\t"
+      "madc.lo.cc.u32 %6, %22, %24, %6; madc.hi.cc.u32 %7, %22, %24, %7;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      "}"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(bi));
+}
+
+// Reduction row: m = e[0] * (-r^-1) mod 2^32; (e,o) += m*r, which clears e[0].  The modulus limbs are immediates.
+CDX_D void mont_row_redc(uint32_t* e, uint32_t* o) {
+  uint32_t m = e[0] * CDX_NP;
+  asm("{\n\t"
+      "mad.lo.cc.u32 %8, %17, %16, %8;    madc.hi.cc.u32 %9, %17, %16, %9;\n\t"
+      "madc.lo.cc.u32 %10, %19, %16, %10; madc.hi.cc.u32 %11, %19, %16, %11;\n\t"
+      "madc.lo.cc.u32 %12, %21, %16, %12; madc.hi.cc.u32 %13, %21, %16, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %16, %14; madc.hi.u32 %15, %23, %16, %15;\n\t"
+      "mad.lo.cc.u32 %0, %18, %16, %0;  madc.hi.cc.u32 %1, %18, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %20, %16, %2; madc.hi.cc.u32 %3, %20, %16, %3;\n\t"
+      "madc.lo.cc.u32 %4, %22, %16, %4; madc.hi.cc.u32 %5, %22, %16, %5;\n\t"
+      "madc.lo.cc.u32 %6, %24, %16, %6; madc.hi.cc.u32 %7, %24, %16, %7;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      "}"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(m), "n"(CDX_N1), "n"(CDX_N0), "n"(CDX_N3), "n"(CDX_N2), "n"(CDX_N5), "n"(CDX_N4), "n"(CDX_N7),
+        "n"(CDX_N6));
+}
+
+// r = e + (o >> 32 limbs aligned as after a row): r[k] = e[k] + o[k+1] with carry
+CDX_D void mont_merge(uint32_t* r, const uint32_t* e, const uint32_t* o) {
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19;"
+      "addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(o[1]),
+        "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+}
+
+// r = a + b (256-bit, carry out discarded: callers keep sums below 2^256)
+CDX_D void add256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19;"
+      "addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+        "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+
+// d = a - r (the modulus); returns 1 if that borrowed (a < r), else 0
+CDX_D uint32_t sub_modulus(uint32_t* d, const uint32_t* a) {
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20;"
+      "subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22; subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24;"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+        "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "n"(CDX_N0),
+        "n"(CDX_N1), "n"(CDX_N2), "n"(CDX_N3), "n"(CDX_N4), "n"(CDX_N5), "n"(CDX_N6), "n"(CDX_N7));
+  return borrow & 1u;
+}
+#elif defined(CDX_HOST_EMUL)
+}  // namespace cdx
+#include "fr_rows_host.h"  // tests/host_emul: C emulation of the six primitives above (unit tests only)
+namespace cdx {
+#else
+#if !defined(__CUDACC__)
+#error "fr.cuh is sm_100a device code; host compilation is only for unit tests with -DCDX_HOST_EMUL"
+#endif
+// host pass of nvcc: declarations only, never called
+void mont_row_first(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
+void mont_row_next(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
+void mont_row_redc(uint32_t*, uint32_t*);
+void mont_merge(uint32_t*, const uint32_t*, const uint32_t*);
+void add256(uint32_t*, const uint32_t*, const uint32_t*);
+uint32_t sub_modulus(uint32_t*, const uint32_t*);
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// field operations built on the primitives (shared between device code and the host-emulated unit tests)
+
+// a*b*2^-256 mod r, lazily reduced (see range discipline at the top)
+CDX_D Fr mont_mul(const Fr& a, const Fr& b) {
+  uint32_t e[8], o[8];
+  mont_row_first(e, o, a.l, b.l[0]);
+  mont_row_redc(e, o);
+  mont_row_next(o, e, a.l, b.l[1]);
+  mont_row_redc(o, e);
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    mont_row_next(e, o, a.l, b.l[i]);
+    mont_row_redc(e, o);
+    mont_row_next(o, e, a.l, b.l[i + 1]);
+    mont_row_redc(o, e);
+  }
+  Fr r;
+  mont_merge(r.l, e, o);
+  return r;
+}
+
+CDX_D Fr mont_sqr(const Fr& a) { return mont_mul(a, a); }
+
+// [0, 2r) -> [0, r)
+CDX_D Fr reduce_once(const Fr& a) {
+  Fr d;
+  uint32_t lt = sub_modulus(d.l, a.l);
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.l[i] = lt ? a.l[i] : d.l[i];
+  return r;
+}
+
+// a + b without reduction (caller guarantees a + b < 2^256)
+CDX_D Fr add_lazy(const Fr& a, const Fr& b) {
+  Fr r;
+  add256(r.l, a.l, b.l);
+  return r;
+}
+
+// inputs < r, output < r
+CDX_D Fr add_mod(const Fr& a, const Fr& b) { return reduce_once(add_lazy(a, b)); }
+CDX_D Fr dbl_mod(const Fr& a) { return reduce_once(add_lazy(a, a)); }
+
+CDX_D Fr fr_zero() {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.l[i] = 0;
+  return r;
+}
+
+// standard form (< 2^256, any value) -> Montgomery form, result < r
+CDX_D Fr to_mont(const Fr& a) {
+  const Fr r2 = {CDX_R2_INIT};
+  // R2 < r is the row operand, a < 2^256 = 5.29 r the per-row multiplier  =>  product < 2r
+  return reduce_once(mont_mul(r2, a));
+}
+
+// Montgomery form (< 2r) -> canonical standard form (< r)
+CDX_D Fr from_mont(const Fr& a) {
+  Fr one = fr_zero();
+  one.l[0] = 1;
+  return reduce_once(mont_mul(a, one));  // a < 2r is the row operand
+}
+
+// small constant c (< 2^32) in Montgomery form
+CDX_D Fr mont_from_u32(uint32_t c) {
+  Fr a = fr_zero();
+  a.l[0] = c;
+  return to_mont(a);
+}
+
+}  // namespace cdx

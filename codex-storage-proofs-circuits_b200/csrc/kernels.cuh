@@ -1,0 +1,249 @@
+// kernels.cuh -- the sm_100a kernels of the slot-commitment path (K1..K6 of SURVEY.md section 2).
+//
+// HBM layout: every retained Merkle layer is a dense array of canonical 32-byte little-endian field elements
+// (what crosses the C ABI), so sampled paths are plain gathers.  Inside a kernel the state is Montgomery-form
+// 8x32-bit limbs in registers; conversion happens at the load/store edge (3 extra modmuls per 240-modmul
+// permutation at most).
+//
+// None of these kernels is HBM-bound: one cell is 2048 B in, 32 B out and 34*240 = 8160 modmuls = 1.1 M
+// integer-multiply instructions.  The bound is the FMA-pipe IMAD.WIDE issue rate ("Roofline").
+#pragma once
+#include "poseidon2.cuh"
+
+namespace cdx {
+
+static __device__ __forceinline__ Fr ld_felt(const uint8_t* p) {   // p is 16-byte aligned
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  Fr r = {{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+  return r;
+}
+
+static __device__ __forceinline__ void st_felt(uint8_t* p, const Fr& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+#define CDX_BLOCK 128
+
+// K1: n independent permutations (BASELINE config 2).           Permutation.hs:40-45
+__global__ void __launch_bounds__(CDX_BLOCK) k_permutation_batch(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x = to_mont(ld_felt(in + 96 * i)), y = to_mont(ld_felt(in + 96 * i + 32)), z = to_mont(ld_felt(in + 96 * i + 64));
+  permute(x, y, z);
+  st_felt(out + 96 * i, from_mont(x));
+  st_felt(out + 96 * i + 32, from_mont(y));
+  st_felt(out + 96 * i + 64, from_mont(z));
+}
+
+// sponge over field elements, one sponge per thread.             Sponge.hs:13-43
+__global__ void __launch_bounds__(CDX_BLOCK) k_sponge_felts(const uint8_t* __restrict__ elems, size_t n_items, uint32_t len, int rate,
+                                                            uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const uint8_t* base = elems + (size_t)32 * len * i;
+  auto get = [&](uint32_t k) { return ld_felt(base + 32 * k); };
+  st_felt(out + 32 * i, from_mont(sponge_elems(get, len, rate)));
+}
+
+// K2: cell sponge, one cell per thread (a warp covers 32 consecutive cells = one 64 KiB block at the default
+// sizes).  Cells are 4-byte aligned and a multiple of 4 bytes long.        blocks/bn254.nim:23-29, Slot.hs:222-228
+__global__ void __launch_bounds__(CDX_BLOCK) k_hash_cells(const uint32_t* __restrict__ data, size_t n_cells, uint32_t cell_words,
+                                                          uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+  AlignedWords ld{data + (size_t)cell_words * i, cell_words};
+  st_felt(out + 32 * i, from_mont(sponge2_bytes(ld, cell_words * 4u)));
+}
+
+// byte strings of arbitrary length/alignment (test-vector suite: n = 0..80).   testvectors.nim:41-46
+__global__ void __launch_bounds__(CDX_BLOCK) k_hash_bytes_any(const uint8_t* __restrict__ data, size_t n_items, uint32_t len,
+                                                              uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  AnyBytes ld{data + (size_t)len * i, len};
+  st_felt(out + 32 * i, from_mont(sponge2_bytes(ld, len)));
+}
+
+// keyed compression batch.                                       Merkle.hs:202-203, merkle/bn254.nim:18
+__global__ void __launch_bounds__(CDX_BLOCK) k_compress_batch(const uint8_t* __restrict__ x, const uint8_t* __restrict__ y,
+                                                              const uint32_t* __restrict__ keys, size_t n, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_felt(out + 32 * i, from_mont(compress_keyed(to_mont(ld_felt(x + 32 * i)), to_mont(ld_felt(y + 32 * i)), keys[i] & 3u)));
+}
+
+// K3: one Merkle level.  out[i] = compress(in[2i], in[2i+1], bottom) ; a trailing single child is paired with 0
+// under key bottom+2 (merkle/bn254.nim:38-53, Merkle.hs:156-178).  The same kernel reduces the forest of block
+// trees (their widths are powers of two, so pairs never straddle two blocks) and every slot/dataset level.
+// singles != 0: every input is a one-leaf tree of its own -> out[i] = compress(in[i], 0, 3) (Merkle.hs:73).
+__global__ void __launch_bounds__(CDX_BLOCK) k_merkle_level(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out,
+                                                            uint32_t bottom, int singles) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n_out = singles ? n : (n + 1) / 2;
+  if (i >= n_out) return;
+  Fr x, y;
+  uint32_t key = bottom;
+  if (singles) {
+    x = to_mont(ld_felt(in + 32 * i));
+    y = fr_zero();
+    key = 3u;
+  } else {
+    x = to_mont(ld_felt(in + 64 * i));
+    if (2 * i + 1 < n) {
+      y = to_mont(ld_felt(in + 64 * i + 32));
+    } else {
+      y = fr_zero();
+      key = bottom + 2u;
+    }
+  }
+  st_felt(out + 32 * i, from_mont(compress_keyed(x, y, key)));
+}
+
+// K4: batched path gather.  One thread per (sample, level, 16-byte half).  Pure data movement.
+//                                                                 merkle.nim:21-42,86-100, types.nim:27-37
+struct PathPlan {
+  const uint8_t* forest[32];   // block-forest level l (local cells >> l nodes), l < block_depth
+  const uint8_t* low[40];      // slot-tree level l for l < top_level: local nodes starting at low_first[l]
+  const uint8_t* top[40];      // slot-tree level l for l >= top_level: all global nodes
+  uint64_t low_first[40];
+  uint64_t low_count[40];
+  uint64_t width[40];          // global width of slot-tree level l
+  uint64_t first_cell, n_local_cells;
+  uint32_t block_depth, slot_depth, top_level, cells_per_block_log2;
+  uint32_t singles;            // one-cell blocks: the block-tree sibling is out of range, i.e. zero (merkle.nim:34)
+};
+
+__global__ void k_gather_paths(PathPlan plan, const uint64_t* __restrict__ cells, uint32_t n_samples, uint32_t max_depth,
+                               uint8_t* __restrict__ out, uint8_t* __restrict__ leaf_out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t per_sample = (max_depth + 1) * 2;             // +1: the leaf itself
+  if (t >= n_samples * per_sample) return;
+  const uint32_t s = t / per_sample, rem = t % per_sample, lvl = rem >> 1, half = rem & 1u;
+  const uint64_t cell = cells[s];
+  const bool mine = cell >= plan.first_cell && cell < plan.first_cell + plan.n_local_cells;
+  const uint64_t lc = cell - plan.first_cell;                  // local cell index (valid if mine)
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (lvl == max_depth) {                                      // leaf slot
+    if (leaf_out == nullptr) return;
+    if (mine) v = reinterpret_cast<const uint4*>(plan.forest[0] + 32 * lc)[half];
+    reinterpret_cast<uint4*>(leaf_out + 32 * (size_t)s)[half] = v;
+    return;
+  }
+  if (mine) {
+    if (lvl < plan.block_depth) {
+      const uint64_t sib = (lc >> lvl) ^ 1ull;                 // block trees are full: sibling always exists
+      if (!plan.singles) v = reinterpret_cast<const uint4*>(plan.forest[lvl] + 32 * sib)[half];
+    } else if (lvl < plan.block_depth + plan.slot_depth) {
+      const uint32_t l = lvl - plan.block_depth;
+      const uint64_t node = (cell >> plan.cells_per_block_log2) >> l;
+      const uint64_t sib = node ^ 1ull;
+      if (sib < plan.width[l]) {                               // out of range -> zero (merkle.nim:34)
+        if (l >= plan.top_level) v = reinterpret_cast<const uint4*>(plan.top[l] + 32 * sib)[half];
+        else if (sib >= plan.low_first[l] && sib < plan.low_first[l] + plan.low_count[l])
+          v = reinterpret_cast<const uint4*>(plan.low[l] + 32 * (sib - plan.low_first[l]))[half];
+      }
+    }
+  }
+  reinterpret_cast<uint4*>(out + 32 * ((size_t)s * max_depth + lvl))[half] = v;
+}
+
+// K5: sampled cell indices.                                       sample/bn254.nim:16-27, types/bn254.nim:47-59
+__global__ void k_cell_indices(const uint8_t* __restrict__ entropy_root /* 64 B */, uint64_t mask, uint32_t n_samples,
+                               uint64_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_samples) return;
+  auto get = [&](uint32_t k) {
+    if (k < 2) return ld_felt(entropy_root + 32 * k);
+    Fr c = fr_zero();
+    c.l[0] = i + 1u;                                           // counters run 1..nSamples
+    return c;
+  };
+  Fr h = from_mont(sponge_elems(get, 3, 2));
+  out[i] = (((uint64_t)h.l[1] << 32) | h.l[0]) & mask;
+}
+
+// K6a: the reference's fake data, one cell per thread.            slot.nim:23-32, Slot.hs:87-96
+__global__ void k_fake_cells(uint64_t seed, uint64_t first_cell, size_t n_cells, uint32_t cell_size, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+  const uint64_t seed1 = seed + 0xdeadcafeull, seed2 = (first_cell + i) + 0x98765432ull;
+  uint64_t s = 1;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + (size_t)cell_size * i);   // cell_size % 4 == 0
+  for (uint32_t w = 0; w < cell_size / 4; ++w) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      s = s * (s + seed1) * (s + seed2) + s * (s ^ 0x5a5a5a5aull) + seed1 * s + (seed2 + 17);
+      s %= 1698428844001831ull;
+      word |= (uint32_t)(s & 0xff) << (8 * b);
+    }
+    dst[w] = word;
+  }
+}
+
+// K6b: counter-based synthetic bytes for the large benchmark slots: word i = splitmix64(seed + first_word + i).
+__global__ void k_fill_synthetic(uint64_t seed, uint64_t first_word, size_t n_words, uint64_t* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) {
+    uint64_t z = seed + first_word + i + 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    out[i] = z ^ (z >> 31);
+  }
+}
+
+// Roofline probe: dependency-light integer multiply streams, ILP 8 per thread.
+//   kind 0: IMAD.WIDE.U32 (64-bit accumulate)   kind 1: IMAD.WIDE.U32.X carry chains of 4 (as in the
+//   Montgomery rows)   kind 2: 32-bit IMAD
+#define CDX_PROBE_OPS_PER_ITER 32
+__global__ void k_probe_imad(int kind, uint32_t iters, uint32_t seed, uint32_t* __restrict__ sink) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  uint32_t r0 = a, r1 = b, r2 = a ^ b, r3 = a + b, r4 = a * 3, r5 = b * 5, r6 = a * 7, r7 = b * 9;
+  uint32_t s0 = 1, s1 = 2, s2 = 3, s3 = 4, s4 = 5, s5 = 6, s6 = 7, s7 = 8;
+  if (kind == 0) {
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile(
+            "{\n\t.reg .u64 t0,t1,t2,t3,t4,t5,t6,t7;\n\t"
+            "mov.b64 t0,{%0,%8}; mov.b64 t1,{%1,%9}; mov.b64 t2,{%2,%10}; mov.b64 t3,{%3,%11};\n\t"
+            "mov.b64 t4,{%4,%12}; mov.b64 t5,{%5,%13}; mov.b64 t6,{%6,%14}; mov.b64 t7,{%7,%15};\n\t"
+            "mad.wide.u32 t0,%16,%17,t0; mad.wide.u32 t1,%16,%17,t1; mad.wide.u32 t2,%16,%17,t2; mad.wide.u32 t3,%16,%17,t3;\n\t"
+            "mad.wide.u32 t4,%16,%17,t4; mad.wide.u32 t5,%16,%17,t5; mad.wide.u32 t6,%16,%17,t6; mad.wide.u32 t7,%16,%17,t7;\n\t"
+            "mov.b64 {%0,%8},t0; mov.b64 {%1,%9},t1; mov.b64 {%2,%10},t2; mov.b64 {%3,%11},t3;\n\t"
+            "mov.b64 {%4,%12},t4; mov.b64 {%5,%13},t5; mov.b64 {%6,%14},t6; mov.b64 {%7,%15},t7;\n\t}"
+            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(s0), "+r"(s1), "+r"(s2),
+              "+r"(s3), "+r"(s4), "+r"(s5), "+r"(s6), "+r"(s7)
+            : "r"(a), "r"(b));
+    }
+  } else if (kind == 1) {
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile(
+            "mad.lo.cc.u32 %0,%16,%17,%0; madc.hi.cc.u32 %8,%16,%17,%8; madc.lo.cc.u32 %1,%16,%17,%1; madc.hi.cc.u32 %9,%16,%17,%9;\n\t"
+            "madc.lo.cc.u32 %2,%16,%17,%2; madc.hi.cc.u32 %10,%16,%17,%10; madc.lo.cc.u32 %3,%16,%17,%3; madc.hi.u32 %11,%16,%17,%11;\n\t"
+            "mad.lo.cc.u32 %4,%16,%17,%4; madc.hi.cc.u32 %12,%16,%17,%12; madc.lo.cc.u32 %5,%16,%17,%5; madc.hi.cc.u32 %13,%16,%17,%13;\n\t"
+            "madc.lo.cc.u32 %6,%16,%17,%6; madc.hi.cc.u32 %14,%16,%17,%14; madc.lo.cc.u32 %7,%16,%17,%7; madc.hi.u32 %15,%16,%17,%15;"
+            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(s0), "+r"(s1), "+r"(s2),
+              "+r"(s3), "+r"(s4), "+r"(s5), "+r"(s6), "+r"(s7)
+            : "r"(a), "r"(b));
+    }
+  } else {
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile(
+            "mad.lo.u32 %0,%0,%8,%9; mad.lo.u32 %1,%1,%8,%9; mad.lo.u32 %2,%2,%8,%9; mad.lo.u32 %3,%3,%8,%9;\n\t"
+            "mad.lo.u32 %4,%4,%8,%9; mad.lo.u32 %5,%5,%8,%9; mad.lo.u32 %6,%6,%8,%9; mad.lo.u32 %7,%7,%8,%9;"
+            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7)
+            : "r"(a), "r"(b));
+    }
+  }
+  uint32_t acc = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7 ^ s0 ^ s1 ^ s2 ^ s3 ^ s4 ^ s5 ^ s6 ^ s7;
+  if (acc == 0x12345678u) sink[0] = acc;   // never true in practice; keeps the loop alive
+}
+
+}  // namespace cdx
