@@ -41,6 +41,29 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+CLI = os.path.join(HERE, "cli")
+HOST_SOURCES = ["proof_input.cpp", "cli.cpp"]
+HOST_HEADERS = ["proof_input.hpp"]
+
+
+def build_host(force: bool = False) -> str:
+    """g++ build of the host-side mirror of reference/nim/proof_input and its `cli`, linked against the in-tree
+    libcodexcommit.so (rpath $ORIGIN, so the pair travels together)."""
+    build_library()
+    deps = [os.path.join(HOST, f) for f in HOST_SOURCES + HOST_HEADERS] + [LIB]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
+        return CLI
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", CLI] + [os.path.join(HOST, s) for s in HOST_SOURCES] + \
+          ["-L" + HERE, "-lcodexcommit", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return CLI
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

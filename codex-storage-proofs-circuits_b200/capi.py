@@ -156,7 +156,8 @@ class Context:
         return out.raw[:96 * n]
 
     def permutation(self, s: Sequence[int]) -> Tuple[int, int, int]:
-        return tuple(unpack(self.permutation_batch_bytes(pack(s))))
+        b = pack(s)
+        return tuple(unpack(self.permutation_batch_bytes(b)))
 
     def permutation_batch_dev(self, d_in: int, d_out: int, n: int, stream: int = 0):
         self._chk(self.lib.cdx_permutation_batch_dev(self.h, d_in, d_out, n, stream))
@@ -186,7 +187,8 @@ class Context:
         n = len(xs)
         karr = (C.c_uint32 * max(n, 1))(*keys)
         out = C.create_string_buffer(32 * n if n else 1)
-        self._chk(self.lib.cdx_compress_batch_host(self.h, _addr(pack(xs)), _addr(pack(ys)), C.addressof(karr), n, C.addressof(out)))
+        bx, by = pack(xs), pack(ys)      # named so the storage outlives the call
+        self._chk(self.lib.cdx_compress_batch_host(self.h, _addr(bx), _addr(by), C.addressof(karr), n, C.addressof(out)))
         return unpack(out.raw[:32 * n])
 
     def compress(self, x: int, y: int, key: int = 0) -> int:
@@ -197,7 +199,8 @@ class Context:
         n = len(leaves)
         total = self.lib.cdx_merkle_total_nodes(n, int(bottom))
         out = C.create_string_buffer(32 * total if total else 1)
-        self._chk(self.lib.cdx_merkle_layers_host(self.h, _addr(pack(leaves)) if n else None, n, int(bottom), C.addressof(out)))
+        bl = pack(leaves)
+        self._chk(self.lib.cdx_merkle_layers_host(self.h, _addr(bl) if n else None, n, int(bottom), C.addressof(out)))
         flat, layers, off, m = unpack(out.raw[:32 * total]), [], 0, n
         for _ in range(self.lib.cdx_merkle_num_layers(n, int(bottom))):
             layers.append(flat[off:off + m])
@@ -208,7 +211,8 @@ class Context:
     def merkle_root(self, leaves: Sequence[int]) -> int:
         out = C.create_string_buffer(32)
         n = len(leaves)
-        self._chk(self.lib.cdx_merkle_root_host(self.h, _addr(pack(leaves)) if n else None, n, out))
+        bl = pack(leaves)
+        self._chk(self.lib.cdx_merkle_root_host(self.h, _addr(bl) if n else None, n, out))
         return b2f(out.raw)
 
     # ---- slots ----
@@ -239,7 +243,8 @@ class Context:
     # ---- sampling / data ----
     def cell_indices(self, entropy: int, slot_root: int, n_cells: int, n_samples: int) -> List[int]:
         out = (C.c_uint64 * max(n_samples, 1))()
-        self._chk(self.lib.cdx_cell_indices(self.h, _addr(f2b(entropy)), _addr(f2b(slot_root)), n_cells, n_samples, C.addressof(out)))
+        be, br = f2b(entropy), f2b(slot_root)
+        self._chk(self.lib.cdx_cell_indices(self.h, _addr(be), _addr(br), n_cells, n_samples, C.addressof(out)))
         return list(out)[:n_samples]
 
     def fake_cells(self, seed: int, first_cell: int, n_cells: int, cell_size: int) -> bytes:

@@ -1,0 +1,471 @@
+// proof_input.cpp -- see proof_input.hpp.  Orchestration, gathering and formatting only; all arithmetic is CUDA.
+#include "proof_input.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace codex {
+
+static void nim_assert(bool cond, const std::string& msg) {
+  if (!cond) throw AssertionDefect(msg);
+}
+
+// ---- nim/types.nim, nim/misc.nim ----------------------------------------------------------------------------
+
+int64_t cellsPerBlock(const GlobalConfig& glob) {   // types.nim:120-123
+  nim_assert(glob.cellSize > 0, "cell size must be positive");
+  const int64_t k = glob.blockSize / glob.cellSize;
+  nim_assert(k * glob.cellSize == glob.blockSize, "block size is not divisible by cell size");
+  return k;
+}
+
+static std::string lower(std::string s) {
+  std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+  return s;
+}
+
+FieldSelect parseField(const std::string& s) {      // types.nim:127-132
+  const std::string l = lower(s);
+  if (l == "bn254") return FieldSelect::BN254;
+  if (l == "goldilocks") return FieldSelect::Goldilocks;
+  throw AssertionDefect("parsefield: unrecognized field `" + s + "`");
+}
+
+HashSelect parseHashFun(const std::string& s) {     // types.nim:134-139
+  const std::string l = lower(s);
+  if (l == "poseidon2") return HashSelect::Poseidon2;
+  if (l == "monolith") return HashSelect::Monolith;
+  throw AssertionDefect("parsefield: unrecognized hash function `" + s + "`");
+}
+
+FieldHashCombo toFieldHashCombo(FieldSelect f, HashSelect h) {   // types.nim:144-157
+  if (f == FieldSelect::BN254) {
+    if (h == HashSelect::Poseidon2) return FieldHashCombo::BN254_Poseidon2;
+    throw AssertionDefect("invalid hash function `Monolith` choice for field `BN254`");
+  }
+  return h == HashSelect::Poseidon2 ? FieldHashCombo::Goldilocks_Poseidon2 : FieldHashCombo::Goldilocks_Monolith;
+}
+
+int floorLog2(int64_t x) {     // misc.nim:10-16
+  int k = -1;
+  for (int64_t y = x; y > 0; y >>= 1) ++k;
+  return k;
+}
+int ceilingLog2(int64_t x) { return x == 0 ? -1 : floorLog2(x - 1) + 1; }   // misc.nim:18-22
+int exactLog2(int64_t x) {     // misc.nim:24-27
+  const int k = ceilingLog2(x);
+  nim_assert(k >= 0 && x == ((int64_t)1 << k), "exactLog2: not a power of two");
+  return k;
+}
+int64_t checkPowerOfTwo(int64_t x, const std::string& what) {   // misc.nim:29-32
+  const int k = ceilingLog2(x);
+  nim_assert(k >= 0 && x == ((int64_t)1 << k), "`" + what + "` is expected to be a power of 2");
+  return x;
+}
+
+MerkleProof padMerkleProof(const MerkleProof& old, int newlen) {   // types.nim:27-37
+  const int pad = newlen - (int)old.merklePath.size();
+  nim_assert(pad >= 0, "padMerkleProof: the path is longer than the requested length");
+  MerkleProof p = old;
+  p.merklePath.resize(newlen, F{});   // zero elements
+  return p;
+}
+
+// ---- nim/types/bn254.nim ------------------------------------------------------------------------------------
+
+static const uint8_t kModulusLE[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                                       0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+
+F intToBN254(int64_t x) {
+  F f{};
+  uint64_t mag = x < 0 ? (uint64_t)(-(x + 1)) + 1 : (uint64_t)x;
+  for (int i = 0; i < 8; ++i) f[i] = (uint8_t)(mag >> (8 * i));
+  if (x < 0) {   // r - |x|
+    int borrow = 0;
+    for (int i = 0; i < 32; ++i) {
+      int d = (int)kModulusLE[i] - (int)f[i] - borrow;
+      borrow = d < 0;
+      f[i] = (uint8_t)(d + (borrow ? 256 : 0));
+    }
+  }
+  return f;
+}
+
+std::string toDecimalF(const F& a) {   // types/bn254.nim:29-33: leading zeros stripped, "0" for zero
+  uint32_t w[8];
+  std::memcpy(w, a.data(), 32);
+  std::string digits;
+  for (;;) {
+    bool nz = false;
+    uint64_t rem = 0;
+    for (int i = 7; i >= 0; --i) {
+      const uint64_t cur = (rem << 32) | w[i];
+      w[i] = (uint32_t)(cur / 1000000000u);
+      rem = cur % 1000000000u;
+      nz |= w[i] != 0;
+    }
+    for (int d = 0; d < 9; ++d) {
+      digits.push_back((char)('0' + rem % 10));
+      rem /= 10;
+    }
+    if (!nz) break;
+  }
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  std::reverse(digits.begin(), digits.end());
+  return digits;
+}
+
+std::string toQuotedDecimalF(const F& a) { return "\"" + toDecimalF(a) + "\""; }
+
+uint64_t extractLowBits(const F& fld, int k) {   // types/bn254.nim:47-59
+  nim_assert(k > 0 && k <= 64, "extractLowBits: k out of range");
+  uint64_t v = 0;
+  std::memcpy(&v, fld.data(), 8);
+  return k == 64 ? v : (v & (((uint64_t)1 << k) - 1));
+}
+
+std::vector<F> elements(const std::vector<uint8_t>& bytes) {   // 31-byte LE chunks of bytes ++ 0x01 ++ 0x00..; Slot.hs:243-270
+  const size_t n = bytes.size() / 31 + 1;
+  std::vector<F> out(n, F{});
+  for (size_t k = 0; k < n; ++k) {
+    const size_t off = 31 * k;
+    const size_t m = std::min<size_t>(31, bytes.size() - off);
+    std::memcpy(out[k].data(), bytes.data() + off, m);
+    if (m < 31) out[k][m] = 0x01;
+  }
+  return out;
+}
+
+// ---- backend ------------------------------------------------------------------------------------------------
+
+Backend::Backend(int device) {
+  const int rc = cdx_ctx_create(device, &ctx_);
+  if (rc != CDX_OK)
+    throw AssertionDefect(std::string("cdx_ctx_create failed: ") + cdx_status_string(rc) + " (this backend needs a CUDA device; there is no CPU path)");
+}
+Backend::~Backend() { cdx_ctx_destroy(ctx_); }
+void Backend::check(int rc, const char* what) const {
+  if (rc != CDX_OK) throw AssertionDefect(std::string(what) + ": " + cdx_last_error(ctx_) + " [" + cdx_status_string(rc) + "]");
+}
+
+// ---- nim/merkle/bn254.nim, nim/merkle.nim -------------------------------------------------------------------
+
+F compressWithKey(Backend& be, int key, const F& x, const F& y) {
+  nim_assert(key >= 0 && key <= 3, "compressWithKey: key must be 0..3");
+  F out{};
+  const uint32_t k = (uint32_t)key;
+  be.check(cdx_compress_batch_host(be.ctx(), x.data(), y.data(), &k, 1, out.data()), "compress");
+  return out;
+}
+
+F merkleDigestBN254(Backend& be, const std::vector<F>& xs) {
+  nim_assert(!xs.empty(), "merkle digest of empty input");
+  F out{};
+  be.check(cdx_merkle_root_host(be.ctx(), xs[0].data(), xs.size(), out.data()), "Merkle.digest");
+  return out;
+}
+
+MerkleTree merkleTreeBN254(Backend& be, const std::vector<F>& xs) {
+  nim_assert(!xs.empty(), "merkle tree of empty input");
+  const size_t total = cdx_merkle_total_nodes(xs.size(), 1);
+  std::vector<F> flat(total);
+  be.check(cdx_merkle_layers_host(be.ctx(), xs[0].data(), xs.size(), 1, flat[0].data()), "merkleTree");
+  MerkleTree t;
+  size_t off = 0, m = xs.size();
+  const int nl = cdx_merkle_num_layers(xs.size(), 1);
+  for (int l = 0; l < nl; ++l) {
+    t.layers.emplace_back(flat.begin() + off, flat.begin() + off + m);
+    off += m;
+    m = (m + 1) / 2;
+  }
+  return t;
+}
+
+int treeDepth(const MerkleTree& t) { return (int)t.layers.size() - 1; }
+int64_t treeNumberOfLeaves(const MerkleTree& t) { return (int64_t)t.layers.at(0).size(); }
+Hash treeRoot(const MerkleTree& t) {
+  nim_assert(!t.layers.empty() && t.layers.back().size() == 1, "treeRoot: topmost layer is not a singleton");
+  return t.layers.back()[0];
+}
+
+MerkleProof merkleProof(const MerkleTree& tree, int64_t index) {   // merkle.nim:21-42
+  const int depth = treeDepth(tree);
+  const int64_t nleaves = treeNumberOfLeaves(tree);
+  nim_assert(index >= 0 && index < nleaves, "merkleProof: index out of range");
+  MerkleProof p;
+  p.merklePath.resize(depth);
+  int64_t k = index, m = nleaves;
+  for (int i = 0; i < depth; ++i) {
+    const int64_t j = k ^ 1;
+    p.merklePath[i] = j < m ? tree.layers[i][j] : F{};
+    k >>= 1;
+    m = (m + 1) >> 1;
+  }
+  p.leafIndex = index;
+  p.leafValue = tree.layers[0][index];
+  p.numberOfLeaves = nleaves;
+  return p;
+}
+
+Hash reconstructRoot(const CompressWithKey& c, const MerkleProof& proof) {   // merkle.nim:51-74
+  int64_t m = proof.numberOfLeaves, j = proof.leafIndex;
+  Hash h = proof.leafValue;
+  int bottomFlag = 1;
+  for (const Hash& p : proof.merklePath) {
+    if (j & 1) h = c(bottomFlag, p, h);
+    else if (j == m - 1) h = c(bottomFlag + 2, h, p);
+    else h = c(bottomFlag, h, p);
+    bottomFlag = 0;
+    j >>= 1;
+    m = (m + 1) >> 1;
+  }
+  return h;
+}
+
+bool checkMerkleProof(const CompressWithKey& c, const Root& root, const MerkleProof& p) { return root == reconstructRoot(c, p); }
+
+MerkleProof mergeMerkleProofs(const CompressWithKey& c, const MerkleProof& bot, const MerkleProof& top) {   // merkle.nim:86-100
+  const Hash botRoot = reconstructRoot(c, bot);
+  nim_assert(botRoot == top.leafValue, "mergeMerkleProofs: bottom root does not match the top leaf");
+  MerkleProof p;
+  p.leafIndex = top.leafIndex * bot.numberOfLeaves + bot.leafIndex;
+  p.leafValue = bot.leafValue;
+  p.numberOfLeaves = bot.numberOfLeaves * top.numberOfLeaves;
+  p.merklePath = bot.merklePath;
+  p.merklePath.insert(p.merklePath.end(), top.merklePath.begin(), top.merklePath.end());
+  return p;
+}
+
+// ---- nim/blocks/bn254.nim -----------------------------------------------------------------------------------
+
+MerkleTree merkleTree(Backend& be, const HashConfig& h, const std::vector<Hash>& what) {
+  nim_assert(h.combo == FieldHashCombo::BN254_Poseidon2, "merkleTree: only BN254/Poseidon2 is implemented by this backend");
+  return merkleTreeBN254(be, what);
+}
+
+Hash hashCell(Backend& be, const HashConfig& h, const GlobalConfig& g, const Cell& cellData) {
+  nim_assert(h.field == FieldSelect::BN254, "hashCell: field must be BN254");
+  nim_assert(h.hashFun == HashSelect::Poseidon2, "hashCell: hash must be Poseidon2");
+  nim_assert((int64_t)cellData.size() == g.cellSize, "cells are expected to be exactly " + std::to_string(g.cellSize) + " bytes");
+  Hash out{};
+  be.check(cdx_hash_bytes_batch_host(be.ctx(), cellData.data(), 1, cellData.size(), out.data()), "hashCell");
+  return out;
+}
+
+static std::vector<Hash> hashBlockCells(Backend& be, const HashConfig& h, const GlobalConfig& g, const Block& blockData) {
+  nim_assert(h.field == FieldSelect::BN254, "field must be BN254");
+  nim_assert((int64_t)blockData.size() == g.blockSize, "network blocks are expected to be exactly" + std::to_string(g.blockSize) + " bytes");
+  const int64_t k = cellsPerBlock(g);
+  std::vector<Hash> leaves(k);
+  be.check(cdx_hash_bytes_batch_host(be.ctx(), blockData.data(), (size_t)k, (size_t)g.cellSize, leaves[0].data()), "hashCell (block)");
+  return leaves;
+}
+
+Hash hashNetworkBlock(Backend& be, const HashConfig& h, const GlobalConfig& g, const Block& blockData) {
+  return merkleDigestBN254(be, hashBlockCells(be, h, g, blockData));
+}
+
+MerkleTree networkBlockTree(Backend& be, const HashConfig& h, const GlobalConfig& g, const Block& blockData) {
+  return merkleTree(be, h, hashBlockCells(be, h, g, blockData));
+}
+
+// ---- nim/sample/bn254.nim -----------------------------------------------------------------------------------
+
+std::vector<int64_t> cellIndices(Backend& be, const HashConfig& h, const Entropy& e, const Root& slotRoot, int64_t numberOfCells, int64_t nSamples) {
+  nim_assert(h.field == FieldSelect::BN254, "cellIndex: field must be BN254");
+  const int lg = ceilingLog2(numberOfCells);
+  nim_assert(lg >= 0 && ((int64_t)1 << lg) == numberOfCells, "for this version, `numberOfCells` is assumed to be a power of two");
+  std::vector<uint64_t> idx((size_t)std::max<int64_t>(nSamples, 0));
+  if (nSamples > 0) be.check(cdx_cell_indices(be.ctx(), e.data(), slotRoot.data(), (uint64_t)numberOfCells, idx.size(), idx.data()), "cellIndices");
+  return std::vector<int64_t>(idx.begin(), idx.end());
+}
+
+int64_t cellIndex(Backend& be, const HashConfig& h, const Entropy& e, const Root& slotRoot, int64_t numberOfCells, int counter) {
+  nim_assert(counter >= 1, "cellIndex: counters start at 1");
+  return cellIndices(be, h, e, slotRoot, numberOfCells, counter).back();
+}
+
+// ---- nim/slot.nim, nim/dataset.nim --------------------------------------------------------------------------
+
+static Cell readFileRange(const std::string& fname, int64_t offset, int64_t len) {   // slot.nim:57-68 (short reads zero-filled)
+  std::ifstream f(fname, std::ios::binary);
+  nim_assert(f.good(), "cannot open slot data file `" + fname + "`");
+  Cell cell((size_t)len, 0);
+  f.seekg(offset);
+  f.read(reinterpret_cast<char*>(cell.data()), len);
+  return cell;
+}
+
+Cell slotLoadCellData(Backend& be, const GlobalConfig& g, const SlotConfig& cfg, CellIdx idx) {
+  if (cfg.dataSrc.kind == DataSourceKind::FakeData) {
+    Cell cell((size_t)g.cellSize);
+    be.check(cdx_fake_cells_host(be.ctx(), cfg.dataSrc.seed, (uint64_t)idx, 1, (size_t)g.cellSize, cell.data()), "genFakeCell");
+    return cell;
+  }
+  nim_assert(g.cellSize <= 16384, "cell size exceeds the reference's 16384-byte file buffer");   // slot.nim:61-62
+  return readFileRange(cfg.dataSrc.filename, g.cellSize * idx, g.cellSize);
+}
+
+Block slotLoadBlockData(Backend& be, const GlobalConfig& g, const SlotConfig& cfg, BlockIdx idx) {
+  const int64_t k = cellsPerBlock(g);
+  if (cfg.dataSrc.kind == DataSourceKind::FakeData) {
+    Block blk((size_t)g.blockSize);
+    be.check(cdx_fake_cells_host(be.ctx(), cfg.dataSrc.seed, (uint64_t)(idx * k), (size_t)k, (size_t)g.cellSize, blk.data()), "genFakeCell (block)");
+    return blk;
+  }
+  return readFileRange(cfg.dataSrc.filename, g.blockSize * idx, g.blockSize);
+}
+
+Seed parametricSlotSeed(Seed seed, SlotIdx k) { return seed + 72 + 1001 * (uint64_t)k; }   // wrap-around, dataset.nim:31-32
+
+SlotConfig slotCfgFromDataSetCfg(const DataSetConfig& d, SlotIdx idx) {
+  nim_assert(idx >= 0 && idx < d.nSlots, "slot index out of range");
+  SlotConfig s;
+  s.nCells = d.nCells;
+  s.nSamples = d.nSamples;
+  s.dataSrc = d.dataSrc;
+  if (d.dataSrc.kind == DataSourceKind::FakeData) s.dataSrc.seed = parametricSlotSeed(d.dataSrc.seed, idx);
+  else s.dataSrc.filename = d.dataSrc.filename + std::to_string(idx) + ".dat";   // dataset.nim:34
+  return s;
+}
+
+Cell dataSetLoadCellData(Backend& be, const GlobalConfig& g, const DataSetConfig& d, SlotIdx s, CellIdx c) {
+  return slotLoadCellData(be, g, slotCfgFromDataSetCfg(d, s), c);
+}
+Block dataSetLoadBlockData(Backend& be, const GlobalConfig& g, const DataSetConfig& d, SlotIdx s, BlockIdx b) {
+  return slotLoadBlockData(be, g, slotCfgFromDataSetCfg(d, s), b);
+}
+
+// ---- nim/gen_input/bn254.nim --------------------------------------------------------------------------------
+
+namespace {
+struct SlotHandle {   // RAII over cdx_slot
+  cdx_slot* h = nullptr;
+  ~SlotHandle() { cdx_slot_free(h); }
+};
+
+// buildSlotTree (gen_input/bn254.nim:21-33) as ONE device commitment; every layer stays in HBM inside the handle
+void commitSlot(Backend& be, const GlobalConfig& g, const SlotConfig& cfg, SlotHandle& out) {
+  const int64_t k = cellsPerBlock(g);
+  const int64_t nblocks = cfg.nCells / k;
+  nim_assert(nblocks * k == cfg.nCells && nblocks > 0, "slot size is not divisible by the block size");
+  if (cfg.dataSrc.kind == DataSourceKind::FakeData) {
+    be.check(cdx_slot_commit_fake(be.ctx(), cfg.dataSrc.seed, (size_t)cfg.nCells, (size_t)g.cellSize, (size_t)g.blockSize, &out.h), "buildSlotTree");
+  } else {
+    Cell bytes = readFileRange(cfg.dataSrc.filename, 0, g.cellSize * cfg.nCells);
+    be.check(cdx_slot_commit_host(be.ctx(), bytes.data(), bytes.size(), (size_t)g.cellSize, (size_t)g.blockSize, &out.h), "buildSlotTree");
+  }
+}
+}  // namespace
+
+SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, const GlobalConfig& globCfg, const DataSetConfig& dsetCfg,
+                                       SlotIdx slotIdx, const Entropy& entropy) {   // gen_input/bn254.nim:35-79
+  nim_assert(hashCfg.combo == FieldHashCombo::BN254_Poseidon2, "only --field=bn254 --hash=poseidon2 is implemented by this backend");
+  const int64_t nslots = dsetCfg.nSlots, ncells = dsetCfg.nCells;
+  const int64_t cpb = cellsPerBlock(globCfg);
+  const int64_t nblocks = ncells / cpb;
+  nim_assert(nblocks * cpb == ncells, "slot size is not divisible by the block size");
+  nim_assert(slotIdx >= 0 && slotIdx < nslots, "slot index out of range");
+
+  // every slot is committed exactly once (the reference rebuilds the sampled slot per sample, :57; same trees)
+  std::vector<Root> slotRoots((size_t)nslots);
+  SlotHandle ours;
+  for (SlotIdx i = 0; i < nslots; ++i) {
+    SlotHandle tmp;
+    SlotHandle& dst = i == slotIdx ? ours : tmp;
+    commitSlot(be, globCfg, slotCfgFromDataSetCfg(dsetCfg, i), dst);
+    be.check(cdx_slot_root(dst.h, slotRoots[(size_t)i].data()), "treeRoot");
+  }
+  const SlotConfig ourSlotCfg = slotCfgFromDataSetCfg(dsetCfg, slotIdx);
+  const Root ourSlotRoot = slotRoots[(size_t)slotIdx];
+
+  const MerkleTree dsetTree = merkleTree(be, hashCfg, slotRoots);                       // :49
+  const Hash dsetRoot = treeRoot(dsetTree);
+  const MerkleProof slotProof = merkleProof(dsetTree, slotIdx);
+
+  const std::vector<int64_t> indices = cellIndices(be, hashCfg, entropy, ourSlotRoot, ncells, dsetCfg.nSamples);   // :53
+
+  uint64_t nc = 0, nb = 0;
+  uint32_t bd = 0, sd = 0;
+  be.check(cdx_slot_shape(ours.h, &nc, &nb, &bd, &sd), "slot shape");
+  nim_assert((int)(bd + sd) <= globCfg.maxDepth, "padMerkleProof: the path is longer than the requested length");
+  const size_t ns = indices.size();
+  std::vector<uint64_t> idx64(indices.begin(), indices.end());
+  std::vector<F> paths(ns * (size_t)globCfg.maxDepth), leaves(ns);
+  if (ns) be.check(cdx_slot_cell_paths(ours.h, idx64.data(), ns, (size_t)globCfg.maxDepth, paths[0].data(), leaves[0].data()), "merkleProof (batched)");
+
+  const CompressWithKey cwk = [&be](int key, const F& x, const F& y) { return compressWithKey(be, key, x, y); };
+  SlotProofInput out;
+  for (size_t s = 0; s < ns; ++s) {
+    const int64_t cellIdx = indices[s], blockIdx = cellIdx / cpb;
+    const F* p = &paths[s * (size_t)globCfg.maxDepth];
+    MerkleProof bot, top;
+    bot.leafIndex = cellIdx % cpb;
+    bot.leafValue = leaves[s];
+    bot.numberOfLeaves = cpb;
+    bot.merklePath.assign(p, p + bd);
+    top.leafIndex = blockIdx;
+    top.numberOfLeaves = nblocks;
+    top.merklePath.assign(p + bd, p + bd + sd);
+    be.check(cdx_slot_read_layer(ours.h, 1, 0, (uint64_t)blockIdx, 1, top.leafValue.data()), "block hash");
+    CellProofInput cpi;
+    cpi.cellData = slotLoadCellData(be, globCfg, ourSlotCfg, cellIdx);                  // :60
+    cpi.merkleProof = padMerkleProof(mergeMerkleProofs(cwk, bot, top), globCfg.maxDepth);   // :63 (asserts bottom root == top leaf)
+    out.proofInputs.push_back(std::move(cpi));
+  }
+  out.dataSetRoot = dsetRoot;
+  out.entropy = entropy;
+  out.nCells = ncells;
+  out.nSlots = nslots;
+  out.slotIndex = slotIdx;
+  out.slotRoot = ourSlotRoot;
+  out.slotProof = padMerkleProof(slotProof, globCfg.maxLog2NSlots);
+  return out;
+}
+
+// ---- nim/json/bn254.nim, nim/json/shared.nim ----------------------------------------------------------------
+
+namespace {
+void writeFieldElems(std::ostream& h, const std::string& prefix, const std::vector<F>& xs) {   // shared.nim:17-25 + bn254.nim:19-20
+  const std::string indent(prefix.size(), ' ');
+  for (size_t i = 0; i < xs.size(); ++i) h << (i == 0 ? prefix + "[ " : indent + ", ") << toQuotedDecimalF(xs[i]) << "\n";
+  h << indent << "]\n";
+}
+template <class T, class Fn>
+void writeList(std::ostream& h, const std::string& prefix, const std::vector<T>& xs, Fn fn) {
+  const std::string indent(prefix.size(), ' ');
+  for (size_t i = 0; i < xs.size(); ++i) fn(h, i == 0 ? prefix + "[ " : indent + ", ", xs[i]);
+  h << indent << "]\n";
+}
+}  // namespace
+
+std::string proofInputToJson(const SlotProofInput& prf) {   // json/bn254.nim:57-74
+  std::ostringstream h;
+  h << "{\n";
+  h << "  \"dataSetRoot\":      " << toQuotedDecimalF(prf.dataSetRoot) << "\n";
+  h << ", \"entropy\":          " << toQuotedDecimalF(prf.entropy) << "\n";
+  h << ", \"nCellsPerSlot\":    " << prf.nCells << "\n";
+  h << ", \"nSlotsPerDataSet\": " << prf.nSlots << "\n";
+  h << ", \"slotIndex\":        " << prf.slotIndex << "\n";
+  h << ", \"slotRoot\":         " << toQuotedDecimalF(prf.slotRoot) << "\n";
+  h << ", \"slotProof\":\n";
+  writeFieldElems(h, "    ", prf.slotProof.merklePath);
+  h << ", \"cellData\":\n";
+  writeList(h, "    ", prf.proofInputs, [](std::ostream& o, const std::string& p, const CellProofInput& c) { writeFieldElems(o, p, elements(c.cellData)); });
+  h << ", \"merklePaths\":\n";
+  writeList(h, "    ", prf.proofInputs, [](std::ostream& o, const std::string& p, const CellProofInput& c) { writeFieldElems(o, p, c.merkleProof.merklePath); });
+  h << "}\n";
+  return h.str();
+}
+
+void exportProofInputBN254(const HashConfig& h, const std::string& fname, const SlotProofInput& prf) {
+  nim_assert(h.field == FieldSelect::BN254, "exportProofInputBN254: field must be BN254");
+  std::ofstream f(fname, std::ios::binary);
+  nim_assert(f.good(), "cannot open `" + fname + "` for writing");
+  f << proofInputToJson(prf);
+}
+
+}  // namespace codex

@@ -1,0 +1,58 @@
+"""The C-ABI library loads and exports every symbol include/codex_commit.h declares (no compute calls: CPU only)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "codex_commit.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cdx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(pkg):
+    names = header_functions()
+    assert len(names) >= 30
+    assert sorted(pkg.capi.SYMBOLS) == names
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(pkg.capi.LIB_PATH)
+    for name in header_functions():
+        assert getattr(lib, name) is not None, name
+    assert pkg.load_library().cdx_abi_version() == 1
+
+
+def test_pure_host_helpers(pkg):
+    lib = pkg.load_library()
+    # layer arithmetic of merkleTreeWorker (merkle/bn254.nim:29-60)
+    assert lib.cdx_merkle_total_nodes(1, 1) == 2 and lib.cdx_merkle_num_layers(1, 1) == 2
+    assert lib.cdx_merkle_total_nodes(1, 0) == 1 and lib.cdx_merkle_num_layers(1, 0) == 1
+    assert lib.cdx_merkle_total_nodes(5, 1) == 5 + 3 + 2 + 1 and lib.cdx_merkle_num_layers(5, 1) == 4
+    assert lib.cdx_merkle_total_nodes(64, 1) == 127
+    assert lib.cdx_status_string(-3).decode().startswith("number of cells")
+
+
+def test_no_device_is_a_loud_error(pkg):
+    """Without a GPU the context cannot be created -- there is no CPU fallback behind the ABI."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.CodexCommitError) as e:
+        pkg.Context(0)
+    assert e.value.status == pkg.capi.CDX_ERR_CUDA
+
+
+def test_product_never_touches_the_oracle():
+    """the product path may not import, link, call or execute anything under oracle/"""
+    pkgdir = os.path.join(ROOT, "codex-storage-proofs-circuits_b200")
+    pat = re.compile(r"(from|import)\s+\.*oracle|oracle/|codex_oracle|coracle|pyoracle")
+    for dp, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert not pat.search(text), f"{os.path.join(dp, f)} references the oracle"

@@ -1,0 +1,76 @@
+"""The device headers' limb-level logic (lazy-reduction bounds, Poseidon2 schedule, 31-byte chunk reader, sponge
+padding) compiled with g++ against a C emulation of the six inline-PTX primitives (tests/host_emul/), compared with
+the oracle.  This is a unit test of shared header code, not a CPU backend: nothing here ships."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emul") / "liblimb.so")
+    src = os.path.join(ROOT, "tests", "host_emul", "limb_logic.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "tests", "host_emul"), "-o", out, src], check=True)
+    return C.CDLL(out)
+
+
+def f2b(x): return int(x).to_bytes(32, "little")
+def b2f(b): return int.from_bytes(b, "little")
+
+
+def test_mont_mul_lazy_bounds(emul):
+    rnd = random.Random(7)
+    rinv = pow(1 << 256, -1, R)
+    out = C.create_string_buffer(32)
+    cases = [(rnd.randrange(2 * R), rnd.randrange(2 * R)) for _ in range(2000)]
+    cases += [(2 * R - 1, 2 * R - 1), (0, 0), (R, R), (R - 1, (1 << 256) - 1), (4 * R - 1, 4 * R - 1), (4 * R, (1 << 256) - 1),
+              ((1 << 256) - R - 1, 5 * R)]
+    for a, b in cases:
+        emul.emul_mont_mul_raw(f2b(a), f2b(b), out)
+        v = b2f(out.raw)
+        assert v % R == a * b * rinv % R
+        assert v <= (a * b >> 256) + R            # documented bound: < a*b/2^256 + r
+        if a < 2 * R and b < 2 * R:
+            assert v < 2 * R
+
+
+def test_permutation_and_compress(emul, orc):
+    rnd = random.Random(8)
+    out = C.create_string_buffer(96)
+    for s in [(0, 1, 2), (R - 1, R - 1, R - 1), (0, 0, 0)] + [tuple(rnd.randrange(R) for _ in range(3)) for _ in range(50)]:
+        emul.emul_permutation(b"".join(f2b(x) for x in s), out)
+        assert tuple(b2f(out.raw[i:i + 32]) for i in (0, 32, 64)) == orc.permutation(s)
+    o32 = C.create_string_buffer(32)
+    for k in range(4):
+        x, y = rnd.randrange(R), rnd.randrange(R)
+        emul.emul_compress(f2b(x), f2b(y), k, o32)
+        assert b2f(o32.raw) == orc.compress(x, y, k)
+
+
+def test_chunk_reader_and_sponge_padding(emul, orc):
+    rnd = random.Random(9)
+    out = C.create_string_buffer(32)
+    for n in list(range(0, 100)) + [128, 256, 2047, 2048, 31 * 66, 31 * 67, 4096]:
+        d = bytes(rnd.randrange(256) for _ in range(n))
+        emul.emul_hash_bytes(d, n, out)
+        assert b2f(out.raw) == orc.hash_bytes(d), n
+        if n % 4 == 0 and n > 0:
+            buf = C.create_string_buffer(d, n)
+            emul.emul_hash_cell_aligned(buf, n, out)
+            assert b2f(out.raw) == orc.hash_bytes(d), n
+    d = b"\xff" * 2048                              # every chunk >= 2^247
+    buf = C.create_string_buffer(d, 2048)
+    emul.emul_hash_cell_aligned(buf, 2048, out)
+    assert b2f(out.raw) == orc.hash_bytes(d)
+    for n in range(0, 9):
+        xs = [rnd.randrange(R) for _ in range(n)]
+        for rate in (1, 2):
+            emul.emul_sponge(b"".join(f2b(x) for x in xs), n, rate, out)
+            assert b2f(out.raw) == orc.sponge(xs, rate)
