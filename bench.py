@@ -1,0 +1,371 @@
+#!/usr/bin/env python3
+"""bench.py -- slot-commit throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W                (N = 1; N > 1 under torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (the CPU path, timed on the host cores)
+
+A "step" is one commitment of the workload: every 2048-byte cell through the Poseidon2 rate-2 sponge, every 64 KiB
+block tree, the slot tree, and the 32-byte root read back.  Workload at N = 1: BASELINE.json configs[2], a single
+10 GiB synthetic slot (163 840 blocks, not a power of two).  At N > 1 each rank holds 10 GiB of one N x 10 GiB slot
+(weak scaling), commits its block range on its own GPU, and one NCCL all-gather of the level-15 sub-tree roots
+(5 x 32 B per rank) feeds the replicated top tree.
+
+  value     whole-job GB/s with the slot bytes already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the host-buffer C-ABI call (pinned host slot -> cdx_slot_commit[_range]_host), H2D of
+            every byte inside the timed region, root read back
+  roofline  the dominant kernel (k_hash_cells) timed alone with CUDA events; bound = FMA-pipe integer multiply
+            issue (DESIGN.md "Roofline"), peak = IMAD.WIDE.U32 rate measured by a probe kernel in the same run;
+            an `hbm` sub-object shows HBM is three orders of magnitude from binding
+  cpu_baseline  oracle (C restatement of the reference path; the Nim toolchain is absent) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PKG = "codex-storage-proofs-circuits_b200"
+CELL, BLOCK = 2048, 65536
+PERMS_PER_BLOCK = 32 * 34 + 31
+MODMUL_PER_PERM = 240
+IMAD_PER_MODMUL = 136                        # 128 IMAD.WIDE.U32 + 8 IMAD (8x32-bit-limb CIOS)
+SEED = 0xC0DE
+
+
+def slot_tree_perms(n_blocks: int) -> int:
+    """compressions in the slot tree over n block hashes (merkle/bn254.nim:38-53)"""
+    total, n, bottom = 0, n_blocks, True
+    while bottom or n > 1:
+        total += (n + 1) // 2
+        n, bottom = (n + 1) // 2, False
+    return total
+
+
+def total_perms(n_blocks: int) -> int:
+    return n_blocks * PERMS_PER_BLOCK + slot_tree_perms(n_blocks)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic bytes on the host (numpy twin of k_fill_synthetic) for the CPU legs
+
+def synthetic_bytes_host(seed: int, first_word: int, n_bytes: int):
+    import numpy as np
+    with np.errstate(over="ignore"):
+        i = np.arange(n_bytes // 8, dtype=np.uint64)
+        z = i + np.uint64((seed + first_word + 0x9e3779b97f4a7c15) & (2**64 - 1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+        z = z ^ (z >> np.uint64(31))
+    return z.view(np.uint8)
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def time_oracle_commit(sample_bytes: int, threads: int, reps: int = 1):
+    """seconds per commitment of `sample_bytes` of the synthetic slot on the host cores (oracle = checker, timed here
+    only as the reported CPU baseline)"""
+    from oracle import coracle
+    coracle.build()
+    buf = synthetic_bytes_host(SEED, 0, sample_bytes)
+    best = None
+    root = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        root, _, _ = coracle.commit_slot((buf.ctypes.data, sample_bytes), CELL, BLOCK, n_threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return best, root
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_id: str):
+        self.gpu_id, self.rows, self.proc, self.thread = gpu_id, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu_id, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+
+def run_reference(args) -> None:
+    """The reference arm: the path's CPU implementation on the box's host cores.  The Nim reference cannot be built
+    here (no nim/nimble; constantine and nim-poseidon2 are un-vendored), so this is the oracle port, all threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    sample = args.ref_sample_mib << 20
+    for _ in range(args.warmup if args.warmup < 2 else 1):      # CPU needs no real warm-up; one pass touches the pages
+        time_oracle_commit(sample, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = time_oracle_commit(sample, threads)
+        t += dt
+    gbs = sample * args.steps / t / 1e9
+    n_blocks_full = int(args.slot_gib * (1 << 30)) // BLOCK * args.gpus
+    line = {
+        "impl": "reference", "metric": "slot commit GB/s (with Poseidon2 perms/s)", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64x4 (BN254 Fr, Montgomery)", "data": "synthetic",
+        "config": {"workload": f"single {args.slot_gib:g} GiB-per-GPU synthetic slot ({n_blocks_full} blocks): cell sponge + block trees + slot root",
+                   "cell_size": CELL, "block_size": BLOCK},
+        "perms_per_s": total_perms(sample // BLOCK) * args.steps / t,
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
+                         "sample": f"first {args.ref_sample_mib} MiB of the workload's synthetic slot per step, {threads} threads over blocks; "
+                                   "C restatement of reference/nim/proof_input (Nim toolchain absent)"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--slot-gib", type=float, default=10.0, help="GiB of slot data per GPU (default: BASELINE config 3, 10 GiB)")
+    ap.add_argument("--ref-sample-mib", type=int, default=64, help="bytes per step of the --impl reference CPU run")
+    ap.add_argument("--cpu-sample-mib", type=int, default=256, help="sample committed once for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    sharded = importlib.import_module(PKG + ".sharded")
+
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)                      # raises if libcodexcommit.so or the GPU is missing: no fallback
+    stream = torch.cuda.ExternalStream(ctx.stream)     # the library's compute stream, so events see its kernels
+
+    blocks_per_gpu = int(args.slot_gib * (1 << 30)) // BLOCK
+    n_bytes = blocks_per_gpu * BLOCK
+    n_total_blocks = blocks_per_gpu * world
+    top_level, ranges = sharded.fixed_ranges(blocks_per_gpu, world)
+    first_block = ranges[rank][0]
+
+    d_slot = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    ctx.fill_synthetic_dev(SEED, first_block * (BLOCK // 8), n_bytes, d_slot.data_ptr())
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def commit_resident():
+        if world == 1:
+            slot = ctx.slot_commit_dev(d_slot.data_ptr(), n_bytes, CELL, BLOCK)
+            root = slot.root                          # 32-byte D2H, synchronises the stream
+            slot.free()
+            return root
+        sh = sharded.GpuShard(ctx.slot_commit_range_dev(d_slot.data_ptr(), n_bytes, CELL, BLOCK, first_block, n_total_blocks, top_level))
+        sharded.exchange_subtree_roots(sh, n_total_blocks, top_level, ranges)
+        root = sh.root
+        sh.free()
+        return root
+
+    def timed(fn, steps):
+        """CUDA events on the library stream + wall clock, both bracketed by barrier + synchronize; max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+        ev = e0.elapsed_time(e1) / 1e3
+        t = torch.tensor([ev, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), out
+
+    gpu_id = str(local_rank)
+    try:
+        gpu_id = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        pass
+
+    # ---- resident-data run (value) ----
+    for _ in range(args.warmup):
+        root = commit_resident()
+    sampler = ClockSampler(gpu_id)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev_s, wall_s, root = timed(commit_resident, args.steps)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_bytes = n_bytes * world
+    value = total_bytes * args.steps / ev_s / 1e9
+    perms_step = total_perms(n_total_blocks)
+
+    # ---- dominant kernel alone (roofline) ----
+    n_cells = n_bytes // CELL
+    d_hashes = torch.empty(n_cells * 32, dtype=torch.uint8, device="cuda")
+    ctx.hash_cells_dev(d_slot.data_ptr(), n_cells, CELL, d_hashes.data_ptr())
+    k_ev, _, _ = timed(lambda: ctx.hash_cells_dev(d_slot.data_ptr(), n_cells, CELL, d_hashes.data_ptr()), args.steps)
+    k_ms = 1e3 * k_ev / args.steps
+    del d_hashes
+    imad_wide, _ = ctx.probe_imad_rate(0)
+    imad_wide_x, _ = ctx.probe_imad_rate(1)
+    kernel_imads = n_cells * 34 * MODMUL_PER_PERM * IMAD_PER_MODMUL
+    achieved = kernel_imads / (k_ms * 1e-3)
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = n_cells * (CELL + 32)
+    roofline = {
+        "kernel": "k_hash_cells", "bound": "int32_imad (FMA-pipe IMAD.WIDE.U32 issue; neither hbm nor tensor)",
+        "achieved": achieved / 1e12, "peak": imad_wide / 1e12, "unit": "T int-multiply instr/s", "frac": achieved / imad_wide,
+        "peak_source": "IMAD.WIDE.U32 probe kernel measured in this run (cdx_probe_imad_rate kind 0)",
+        "peak_carry_chain": imad_wide_x / 1e12, "frac_of_carry_chain_peak": achieved / imad_wide_x,
+        "kernel_ms": k_ms, "algorithmic_imads_per_launch": kernel_imads, "modmuls_per_s": achieved / IMAD_PER_MODMUL,
+        "traffic": None,
+        "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg_bytes},
+    }
+    del_traffic = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu capture, if any
+    if os.path.exists(del_traffic):
+        try:
+            roofline["traffic"] = json.load(open(del_traffic))
+        except Exception:
+            pass
+
+    # ---- end to end through the host-buffer ABI ----
+    e2e = None
+    if not args.no_e2e:
+        h_slot = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+        h_slot.copy_(d_slot)
+        torch.cuda.synchronize()
+        h_np = h_slot.numpy()
+
+        def commit_host():
+            if world == 1:
+                slot = ctx.slot_commit_host(h_np, CELL, BLOCK)
+                r = slot.root
+                slot.free()
+                return r
+            sh = sharded.GpuShard(ctx.slot_commit_range_host(h_np, CELL, BLOCK, first_block, n_total_blocks, top_level))
+            sharded.exchange_subtree_roots(sh, n_total_blocks, top_level, ranges)
+            r = sh.root
+            sh.free()
+            return r
+
+        for _ in range(min(args.warmup, 2)):
+            r2 = commit_host()
+        _, e2e_wall, r2 = timed(commit_host, args.steps)
+        assert r2 == root, "host-buffer path and resident path disagree on the slot root"
+        e2e = {"value": total_bytes * args.steps / e2e_wall / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n_bytes * world, "d2h_bytes_per_step": 32 * world,
+               "ms_per_step": 1e3 * e2e_wall / args.steps,
+               "api": "cdx_slot_commit_host" if world == 1 else "cdx_slot_commit_range_host + NCCL all-gather + cdx_slot_set_top_dev",
+               "timing": "wall clock bracketed by barrier + cudaDeviceSynchronize, max over ranks"}
+        del h_slot
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = host_threads()
+        sample = min(args.cpu_sample_mib << 20, n_bytes)
+        dt, cpu_root = time_oracle_commit(sample, threads)
+        # the sample doubles as a parity check at bench size: GPU root of the same prefix must equal the oracle's
+        with ctx.slot_commit_dev(d_slot.data_ptr(), sample, CELL, BLOCK) as s:
+            assert s.root == cpu_root, "GPU and oracle disagree on the sample root"
+        cpu = {"value": sample / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
+               "perms_per_s": total_perms(sample // BLOCK) / dt,
+               "sample": f"first {sample >> 20} MiB of the same synthetic slot, one commitment, {threads} threads over blocks "
+                         "(C restatement of reference/nim/proof_input; Nim toolchain absent); root checked equal to the GPU's"}
+
+    if rank == 0:
+        line = {
+            "metric": "slot commit GB/s (with Poseidon2 perms/s)", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (BN254 Fr, 256-bit Montgomery integers)", "data": "synthetic",
+            "config": {"workload": f"single {args.slot_gib:g} GiB-per-GPU synthetic slot ({n_total_blocks} blocks of 64 KiB, 2048-byte cells): "
+                                   "cell sponge + block trees + slot tree + root",
+                       "bytes_per_step": total_bytes, "cell_size": CELL, "block_size": BLOCK, "seed": SEED,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks x block-range shards, all-gather of level-{top_level} roots",
+                       "l2": "inputs (10 GiB per GPU) are larger than L2; no flush needed"},
+            "perms_per_s": perms_step * args.steps / ev_s, "perms_per_step": perms_step,
+            "slot_root": hex(root), "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,7 @@ SYMBOLS = {
     "cdx_permutation_batch_dev": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cdx_sponge_felts_batch_host": (_int, [_vp, _vp, _sz, _sz, _int, _vp]),
     "cdx_hash_bytes_batch_host": (_int, [_vp, _vp, _sz, _sz, _vp]),
+    "cdx_hash_cells_dev": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "cdx_compress_batch_host": (_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "cdx_merkle_total_nodes": (_sz, [_sz, _int]),
     "cdx_merkle_num_layers": (_int, [_sz, _int]),
@@ -40,6 +41,8 @@ SYMBOLS = {
     "cdx_slot_commit_dev": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _pp]),
     "cdx_slot_commit_fake": (_int, [_vp, _u64, _sz, _sz, _sz, _pp]),
     "cdx_slot_commit_range_dev": (_int, [_vp, _vp, _sz, _sz, _sz, _u64, _u64, _int, _vp, _pp]),
+    "cdx_slot_commit_range_host": (_int, [_vp, _vp, _sz, _sz, _sz, _u64, _u64, _int, _pp]),
+    "cdx_slot_subtree_roots_copy_dev": (_int, [_vp, _vp, _vp]),
     "cdx_slot_subtree_root_count": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "cdx_slot_subtree_roots_dev": (_vp, [_vp]),
     "cdx_slot_set_top_dev": (_int, [_vp, _vp, _u64, _vp]),
@@ -240,6 +243,17 @@ class Context:
                                                      n_total_blocks, top_level, stream, C.byref(h)))
         return Slot(self, h)
 
+    def slot_commit_range_host(self, data, cell_size: int, block_size: int, first_block: int, n_total_blocks: int,
+                               top_level: int, n_bytes: Optional[int] = None) -> "Slot":
+        nb = n_bytes if n_bytes is not None else (data.nbytes if hasattr(data, "nbytes") else len(data))
+        h = C.c_void_p()
+        self._chk(self.lib.cdx_slot_commit_range_host(self.h, _addr(data), nb, cell_size, block_size, first_block,
+                                                      n_total_blocks, top_level, C.byref(h)))
+        return Slot(self, h)
+
+    def hash_cells_dev(self, d_data: int, n_cells: int, cell_size: int, d_out: int, stream: int = 0):
+        self._chk(self.lib.cdx_hash_cells_dev(self.h, d_data, n_cells, cell_size, d_out, stream))
+
     # ---- sampling / data ----
     def cell_indices(self, entropy: int, slot_root: int, n_cells: int, n_samples: int) -> List[int]:
         out = (C.c_uint64 * max(n_samples, 1))()
@@ -318,6 +332,9 @@ class Slot:
         first, cnt = C.c_uint64(), C.c_uint64()
         self.ctx._chk(self.ctx.lib.cdx_slot_subtree_root_count(self.h, C.byref(first), C.byref(cnt)))
         return first.value, cnt.value, (self.ctx.lib.cdx_slot_subtree_roots_dev(self.h) or 0)
+
+    def subtree_roots_copy_dev(self, d_dst: int, stream: int = 0):
+        self.ctx._chk(self.ctx.lib.cdx_slot_subtree_roots_copy_dev(self.h, d_dst, stream))
 
     def set_top_dev(self, d_nodes: int, n_nodes: int, stream: int = 0):
         self.ctx._chk(self.ctx.lib.cdx_slot_set_top_dev(self.h, d_nodes, n_nodes, stream))

@@ -202,6 +202,16 @@ extern "C" int cdx_hash_bytes_batch_host(cdx_ctx* ctx, const uint8_t* data, size
   return CDX_OK;
 }
 
+extern "C" int cdx_hash_cells_dev(cdx_ctx* ctx, const void* d_data, size_t n_cells, size_t cell_size, void* d_out, void* stream) {
+  if (!ctx || !d_data || !d_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (cell_size == 0 || cell_size % 4 || cell_size > (1u << 30)) return fail(ctx, CDX_ERR_SIZE, "cell size %zu must be a non-zero multiple of 4", cell_size);
+  if ((uintptr_t)d_data % 16 || (uintptr_t)d_out % 16) return fail(ctx, CDX_ERR_ARG, "buffers must be 16-byte aligned");
+  if (n_cells == 0) return CDX_OK;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  LAUNCH(ctx, k_hash_cells, n_cells, st, (const uint32_t*)d_data, n_cells, (uint32_t)(cell_size / 4), (uint8_t*)d_out);
+  return CDX_OK;
+}
+
 extern "C" int cdx_compress_batch_host(cdx_ctx* ctx, const uint8_t* x, const uint8_t* y, const uint32_t* keys, size_t n, uint8_t* out) {
   if (!ctx || !x || !y || !keys || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
   for (size_t i = 0; i < n; ++i)
@@ -496,23 +506,30 @@ static int ensure_stage(cdx_ctx* ctx, size_t bytes) {
   return CDX_OK;
 }
 
-// Host-resident slot: the bytes stream through two device tiles; the copy of tile t+1 (copy stream) overlaps the
-// cell sponge of tile t (compute stream).  Only hashes stay resident.
-extern "C" int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
+// Host-resident slot (or block range of one): the bytes stream through two device tiles; the copy of tile t+1 (copy
+// stream) overlaps the cell sponge of tile t (compute stream).  Only hashes stay resident.
+static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block,
+                             uint64_t n_total_blocks, int top_level, bool whole_slot, cdx_slot** out) {
   if (!ctx || !data || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
   *out = nullptr;
   int rc = check_shape(ctx, n_bytes, cell_size, block_size);
   if (rc) return rc;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t n_blocks = n_bytes / block_size;
-  size_t tile_blocks = ((size_t)64 << 20) / block_size;        // 64 MiB tiles
+  if (whole_slot) n_total_blocks = n_blocks;
+  // Tile = 256 MiB: 131 072 cells of 2 KiB, i.e. one full wave of the cell-sponge kernel on 148 SMs (7 CTAs of 128
+  // threads per SM at 70 registers); smaller tiles leave SMs idle, larger ones only add exposed first-copy latency.
+  // Slots below 1 GiB are cut in four so that the copy still overlaps.
+  size_t tile_bytes_target = (size_t)256 << 20;
+  if (n_bytes < ((size_t)1 << 30)) tile_bytes_target = n_bytes / 4 > ((size_t)16 << 20) ? n_bytes / 4 : ((size_t)16 << 20);
+  size_t tile_blocks = tile_bytes_target / block_size;
   if (tile_blocks == 0) tile_blocks = 1;
   if (tile_blocks > n_blocks) tile_blocks = n_blocks;
   const size_t tile_bytes = tile_blocks * block_size;
   rc = ensure_stage(ctx, tile_bytes);
   if (rc) return rc;
   cdx_slot* s = nullptr;
-  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, 0, n_blocks, 0, ctx->stream, &s);
+  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, first_block, n_total_blocks, top_level, ctx->stream, &s);
   if (rc) return rc;
   const size_t cpb = block_size / cell_size;
   auto body = [&]() -> int {
@@ -531,8 +548,10 @@ extern "C" int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_
     }
     int r = build_local_trees(s);
     if (r) return r;
-    r = build_top(s, s->low[0], true);
-    if (r) return r;
+    if (whole_slot) {
+      r = build_top(s, s->low[0], true);
+      if (r) return r;
+    }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CDX_OK;
   };
@@ -545,6 +564,15 @@ extern "C" int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_
   }
   *out = s;
   return CDX_OK;
+}
+
+extern "C" int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
+  return commit_host_range(ctx, data, n_bytes, cell_size, block_size, 0, 0, 0, true, out);
+}
+
+extern "C" int cdx_slot_commit_range_host(cdx_ctx* ctx, const uint8_t* data, size_t n_local_bytes, size_t cell_size, size_t block_size,
+                                          uint64_t first_block, uint64_t n_total_blocks, int top_level, cdx_slot** out) {
+  return commit_host_range(ctx, data, n_local_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, false, out);
 }
 
 extern "C" int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells, size_t cell_size, size_t block_size, cdx_slot** out) {
@@ -578,6 +606,16 @@ extern "C" int cdx_slot_subtree_root_count(const cdx_slot* s, uint64_t* first_no
 }
 
 extern "C" const void* cdx_slot_subtree_roots_dev(const cdx_slot* s) { return s ? s->low[s->top_level] : nullptr; }
+
+extern "C" int cdx_slot_subtree_roots_copy_dev(const cdx_slot* s, void* d_dst, void* stream) {
+  if (!s || !d_dst) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+  if (st != s->stream) CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(d_dst, s->low[s->top_level], 32 * s->low_count[s->top_level], cudaMemcpyDeviceToDevice, st));
+  return CDX_OK;
+}
 
 extern "C" int cdx_slot_set_top_dev(cdx_slot* s, const void* d_level_nodes, uint64_t n_level_nodes, void* stream) {
   if (!s || !d_level_nodes) return CDX_ERR_ARG;

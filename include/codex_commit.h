@@ -72,6 +72,11 @@ int cdx_sponge_felts_batch_host(cdx_ctx* ctx, const uint8_t* elems, size_t n_ite
  * testvectors.nim:45; reference/haskell/src/Slot.hs:222-270. */
 int cdx_hash_bytes_batch_host(cdx_ctx* ctx, const uint8_t* data, size_t n_items, size_t len, uint8_t* out);
 
+/* Cell hashes only, device to device: n_cells cells of cell_size bytes (a multiple of 4) at d_data -> n_cells field
+ * elements at d_out.  This is the dominant kernel of the path (34 permutations per 2048-byte cell); bench.py times
+ * it alone for the roofline.  Replaces: the hashCell loop of networkBlockTree -- nim/blocks/bn254.nim:23-29,63. */
+int cdx_hash_cells_dev(cdx_ctx* ctx, const void* d_data, size_t n_cells, size_t cell_size, void* d_out, void* stream);
+
 /* out[i] = perm(x[i], y[i], keys[i])[0], keys in 0..3.
  * Replaces: compress(x, y, key=) via compressWithkey -- nim/merkle/bn254.nim:18,50,53;
  * reference/haskell/src/Poseidon2/Merkle.hs:202-203. */
@@ -118,7 +123,11 @@ int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells, size_t cel
  * conventions are nim/merkle/bn254.nim:29-60 with the odd-node rule applied to the GLOBAL layer width.) */
 int cdx_slot_commit_range_dev(cdx_ctx* ctx, const void* d_data, size_t n_local_bytes, size_t cell_size, size_t block_size,
                               uint64_t first_block, uint64_t n_total_blocks, int top_level, void* stream, cdx_slot** out);
+int cdx_slot_commit_range_host(cdx_ctx* ctx, const uint8_t* data, size_t n_local_bytes, size_t cell_size, size_t block_size,
+                               uint64_t first_block, uint64_t n_total_blocks, int top_level, cdx_slot** out);
 int cdx_slot_subtree_root_count(const cdx_slot* slot, uint64_t* first_node, uint64_t* n_nodes);
+/* copy this rank's level-top_level nodes into a caller buffer (e.g. a torch tensor handed to NCCL all-gather) */
+int cdx_slot_subtree_roots_copy_dev(const cdx_slot* slot, void* d_dst, void* stream);
 /* device pointer to this rank's level-top_level nodes (n_nodes * 32 bytes), for NCCL */
 const void* cdx_slot_subtree_roots_dev(const cdx_slot* slot);
 int cdx_slot_set_top_dev(cdx_slot* slot, const void* d_level_nodes, uint64_t n_level_nodes, void* stream);
