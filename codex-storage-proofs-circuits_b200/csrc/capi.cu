@@ -102,6 +102,14 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   ctx->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) {   // keep freed tree buffers in the pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, device);
+    if (e == cudaSuccess) {
+      uint64_t never = UINT64_MAX;
+      e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+    }
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -133,13 +141,20 @@ extern "C" const char* cdx_last_error(const cdx_ctx* ctx) { return ctx ? ctx->er
 extern "C" uint64_t cdx_launch_count(const cdx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* cdx_ctx_stream(const cdx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
-// scoped device buffer for the *_host entry points
+// Scoped device buffer for the *_host entry points.  Stream-ordered allocation from the device's default memory
+// pool (release threshold raised to "never" in cdx_ctx_create): cudaMalloc/cudaFree cost tens to hundreds of
+// milliseconds for tree-sized buffers on this platform and serialise the device, cudaMallocAsync/cudaFreeAsync
+// reuse pooled memory in microseconds.
 struct DevBuf {
   void* p = nullptr;
+  cudaStream_t st = nullptr;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
   }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+    st = stream;
+    return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+  }
   uint8_t* u8() const { return static_cast<uint8_t*>(p); }
 };
 
@@ -158,8 +173,8 @@ extern "C" int cdx_permutation_batch_host(cdx_ctx* ctx, const uint8_t* in, uint8
   if (n == 0) return CDX_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf di, dout;
-  CU_TRY(ctx, di.alloc(96 * n));
-  CU_TRY(ctx, dout.alloc(96 * n));
+  CU_TRY(ctx, di.alloc(96 * n, ctx->stream));
+  CU_TRY(ctx, dout.alloc(96 * n, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(di.p, in, 96 * n, cudaMemcpyHostToDevice, ctx->stream));
   int rc = cdx_permutation_batch_dev(ctx, di.p, dout.p, n, ctx->stream);
   if (rc) return rc;
@@ -175,8 +190,8 @@ extern "C" int cdx_sponge_felts_batch_host(cdx_ctx* ctx, const uint8_t* elems, s
   if (n_items == 0) return CDX_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf di, dout;
-  CU_TRY(ctx, di.alloc(32 * len * n_items));
-  CU_TRY(ctx, dout.alloc(32 * n_items));
+  CU_TRY(ctx, di.alloc(32 * len * n_items, ctx->stream));
+  CU_TRY(ctx, dout.alloc(32 * n_items, ctx->stream));
   if (len) CU_TRY(ctx, cudaMemcpyAsync(di.p, elems, 32 * len * n_items, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, k_sponge_felts, n_items, ctx->stream, di.u8(), n_items, (uint32_t)len, rate, dout.u8());
   CU_TRY(ctx, cudaMemcpyAsync(out, dout.p, 32 * n_items, cudaMemcpyDeviceToHost, ctx->stream));
@@ -190,8 +205,8 @@ extern "C" int cdx_hash_bytes_batch_host(cdx_ctx* ctx, const uint8_t* data, size
   if (n_items == 0) return CDX_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf di, dout;
-  CU_TRY(ctx, di.alloc(len * n_items));
-  CU_TRY(ctx, dout.alloc(32 * n_items));
+  CU_TRY(ctx, di.alloc(len * n_items, ctx->stream));
+  CU_TRY(ctx, dout.alloc(32 * n_items, ctx->stream));
   if (len) CU_TRY(ctx, cudaMemcpyAsync(di.p, data, len * n_items, cudaMemcpyHostToDevice, ctx->stream));
   if (len % 4 == 0 && len > 0)   // cudaMalloc'd base is 256-byte aligned, so every item is word aligned
     LAUNCH(ctx, k_hash_cells, n_items, ctx->stream, (const uint32_t*)di.p, n_items, (uint32_t)(len / 4), dout.u8());
@@ -219,10 +234,10 @@ extern "C" int cdx_compress_batch_host(cdx_ctx* ctx, const uint8_t* x, const uin
   if (n == 0) return CDX_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf dx, dy, dk, dout;
-  CU_TRY(ctx, dx.alloc(32 * n));
-  CU_TRY(ctx, dy.alloc(32 * n));
-  CU_TRY(ctx, dk.alloc(4 * n));
-  CU_TRY(ctx, dout.alloc(32 * n));
+  CU_TRY(ctx, dx.alloc(32 * n, ctx->stream));
+  CU_TRY(ctx, dy.alloc(32 * n, ctx->stream));
+  CU_TRY(ctx, dk.alloc(4 * n, ctx->stream));
+  CU_TRY(ctx, dout.alloc(32 * n, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(dx.p, x, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(dy.p, y, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(dk.p, keys, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -277,7 +292,7 @@ extern "C" int cdx_merkle_layers_host(cdx_ctx* ctx, const uint8_t* leaves, size_
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t total = cdx_merkle_total_nodes(n, bottom_layer);
   DevBuf d;
-  CU_TRY(ctx, d.alloc(32 * total));
+  CU_TRY(ctx, d.alloc(32 * total, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(d.p, leaves, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
   int rc = merkle_layers_on_device(ctx, d.u8(), n, bottom_layer != 0, ctx->stream);
   if (rc) return rc;
@@ -292,7 +307,7 @@ extern "C" int cdx_merkle_root_host(cdx_ctx* ctx, const uint8_t* leaves, size_t 
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t total = cdx_merkle_total_nodes(n, 1);
   DevBuf d;
-  CU_TRY(ctx, d.alloc(32 * total));
+  CU_TRY(ctx, d.alloc(32 * total, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(d.p, leaves, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
   int rc = merkle_layers_on_device(ctx, d.u8(), n, true, ctx->stream);
   if (rc) return rc;
@@ -313,10 +328,9 @@ static uint32_t log2_u64(uint64_t x) {
 extern "C" void cdx_slot_free(cdx_slot* s) {
   if (!s) return;
   if (s->ctx) cudaSetDevice(s->ctx->device);
-  if (s->stream) cudaStreamSynchronize(s->stream);
-  if (s->d_forest) cudaFree(s->d_forest);
-  if (s->d_low) cudaFree(s->d_low);
-  if (s->d_top) cudaFree(s->d_top);
+  if (s->d_forest) cudaFreeAsync(s->d_forest, s->stream);   // ordered after everything queued on the slot's stream
+  if (s->d_low) cudaFreeAsync(s->d_low, s->stream);
+  if (s->d_top) cudaFreeAsync(s->d_top, s->stream);
   delete s;
 }
 
@@ -391,8 +405,8 @@ static int slot_alloc(cdx_ctx* ctx, uint64_t n_local_blocks, size_t cell_size, s
     l_off.push_back(low_nodes);
     low_nodes += s->low_count[l];
   }
-  cudaError_t e = cudaMalloc((void**)&s->d_forest, 32 * forest_nodes);
-  if (e == cudaSuccess && low_nodes) e = cudaMalloc((void**)&s->d_low, 32 * low_nodes);
+  cudaError_t e = cudaMallocAsync((void**)&s->d_forest, 32 * forest_nodes, st);
+  if (e == cudaSuccess && low_nodes) e = cudaMallocAsync((void**)&s->d_low, 32 * low_nodes, st);
   if (e != cudaSuccess) {
     cdx_slot_free(s);
     return fail(ctx, CDX_ERR_ALLOC, "cudaMalloc of %zu tree nodes failed: %s", forest_nodes + low_nodes, cudaGetErrorString(e));
@@ -434,10 +448,10 @@ static int build_top(cdx_slot* s, const uint8_t* d_level_nodes, bool alias) {
     if (!(alias && l == T)) nodes += s->width[l];
   }
   if (s->d_top) {
-    cudaFree(s->d_top);
+    cudaFreeAsync(s->d_top, s->stream);
     s->d_top = nullptr;
   }
-  if (nodes) CU_TRY(ctx, cudaMalloc((void**)&s->d_top, 32 * nodes));
+  if (nodes) CU_TRY(ctx, cudaMallocAsync((void**)&s->d_top, 32 * nodes, s->stream));
   s->top.assign(s->slot_depth + 1, nullptr);
   for (uint32_t l = T; l <= s->slot_depth; ++l) s->top[l] = s->d_top + 32 * off[l - T];
   if (alias) {
@@ -583,7 +597,7 @@ extern "C" int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells,
   if (rc) return rc;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf d;
-  CU_TRY(ctx, d.alloc(n_cells * cell_size));
+  CU_TRY(ctx, d.alloc(n_cells * cell_size, ctx->stream));
   rc = cdx_fake_cells_dev(ctx, seed, 0, n_cells, cell_size, d.p, ctx->stream);
   if (rc) return rc;
   cdx_slot* s = nullptr;
@@ -715,9 +729,9 @@ extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indic
   plan.top_level = s->top_level;
   plan.cells_per_block_log2 = s->cpb_log2;
   DevBuf d_idx, d_out, d_leaf;
-  CU_TRY(ctx, d_idx.alloc(8 * n_samples));
-  CU_TRY(ctx, d_out.alloc(32 * n_samples * max_depth));
-  CU_TRY(ctx, d_leaf.alloc(32 * n_samples));
+  CU_TRY(ctx, d_idx.alloc(8 * n_samples, s->stream));
+  CU_TRY(ctx, d_out.alloc(32 * n_samples * max_depth, s->stream));
+  CU_TRY(ctx, d_leaf.alloc(32 * n_samples, s->stream));
   CU_TRY(ctx, cudaMemcpyAsync(d_idx.p, cell_indices, 8 * n_samples, cudaMemcpyHostToDevice, s->stream));
   const size_t threads = n_samples * (max_depth + 1) * 2;
   k_gather_paths<<<grid_for(threads, 256), 256, 0, s->stream>>>(plan, (const uint64_t*)d_idx.p, (uint32_t)n_samples, (uint32_t)max_depth,
@@ -739,8 +753,8 @@ extern "C" int cdx_cell_indices(cdx_ctx* ctx, const uint8_t entropy[32], const u
   if (n_samples > 0xffffffffu) return fail(ctx, CDX_ERR_SIZE, "too many samples");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf d_in, d_out;
-  CU_TRY(ctx, d_in.alloc(64));
-  CU_TRY(ctx, d_out.alloc(8 * n_samples));
+  CU_TRY(ctx, d_in.alloc(64, ctx->stream));
+  CU_TRY(ctx, d_out.alloc(8 * n_samples, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(d_in.p, entropy, 32, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(d_in.u8() + 32, slot_root, 32, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(ctx, k_cell_indices, n_samples, ctx->stream, d_in.u8(), n_cells - 1, (uint32_t)n_samples, (uint64_t*)d_out.p);
@@ -763,7 +777,7 @@ extern "C" int cdx_fake_cells_host(cdx_ctx* ctx, uint64_t seed, uint64_t first_c
   if (n_cells == 0) return CDX_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf d;
-  CU_TRY(ctx, d.alloc(n_cells * cell_size));
+  CU_TRY(ctx, d.alloc(n_cells * cell_size, ctx->stream));
   int rc = cdx_fake_cells_dev(ctx, seed, first_cell, n_cells, cell_size, d.p, ctx->stream);
   if (rc) return rc;
   CU_TRY(ctx, cudaMemcpyAsync(out, d.p, n_cells * cell_size, cudaMemcpyDeviceToHost, ctx->stream));
@@ -793,7 +807,7 @@ extern "C" int cdx_probe_imad_rate(cdx_ctx* ctx, int kind, double* ops_per_secon
   if (kind < 0 || kind > 2) return fail(ctx, CDX_ERR_ARG, "kind must be 0, 1 or 2");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   DevBuf sink;
-  CU_TRY(ctx, sink.alloc(4));
+  CU_TRY(ctx, sink.alloc(4, ctx->stream));
   const unsigned blocks = (unsigned)ctx->sm_count * 8, threads = 256;
   const uint32_t iters = 8192;
   cudaEvent_t e0, e1;
