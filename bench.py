@@ -297,10 +297,13 @@ def main() -> None:
         "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg_bytes},
     }
-    del_traffic = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes per launch from the committed ncu capture, if any
-    if os.path.exists(del_traffic):
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")    # dram bytes from the committed `ncu --set full` capture
+    if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(del_traffic))
+            tj = json.load(open(traffic_file))
+            roofline["traffic"] = tj["dram_bytes_per_slot_byte"] * n_bytes
+            roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of k_hash_cells, scaled per slot byte from the "
+                                        f"{tj['slot_bytes_in_launch'] >> 30} GiB launch captured in {tj['source']}")
         except Exception:
             pass
 

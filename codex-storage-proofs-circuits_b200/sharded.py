@@ -30,16 +30,25 @@ def level_width(n_blocks: int, level: int) -> int:
     return w
 
 
-def plan_block_ranges(n_total_blocks: int, world_size: int, min_chunks_per_rank: int = 8) -> Tuple[int, List[Tuple[int, int]]]:
+def plan_block_ranges(n_total_blocks: int, world_size: int, max_imbalance: float = 0.01,
+                      min_chunks_per_rank: int = 1) -> Tuple[int, List[Tuple[int, int]]]:
     """Choose the exchange level T and a contiguous, 2^T-aligned block range per rank.
 
-    T is the largest level that still leaves >= min_chunks_per_rank chunks per rank (so the imbalance from whole
-    chunks stays below 1/min_chunks_per_rank) -- and 0 when the slot is too small for that.  Ranks with no blocks
-    get (first, 0)."""
+    T is the largest level for which splitting the 2^T-block chunks evenly leaves the most loaded rank within
+    `max_imbalance` of the ideal share (100 GiB over 8 GPUs: T = 13, 25 chunks of 8192 blocks per rank) -- the
+    larger T, the fewer sub-tree roots are exchanged and the smaller the replicated top tree.  Falls back to
+    T = 0 (exchange raw block hashes) for slots too small to balance.  Ranks with no blocks get (first, 0)."""
     assert n_total_blocks >= 1 and world_size >= 1
-    t = 0
-    while ceil_div(n_total_blocks, 1 << (t + 1)) >= min_chunks_per_rank * world_size:
-        t += 1
+    best_t = 0
+    t = max(0, (n_total_blocks - 1).bit_length())
+    while t > 0:
+        n_chunks = ceil_div(n_total_blocks, 1 << t)
+        heaviest = min(ceil_div(n_chunks, world_size) << t, n_total_blocks)
+        if n_chunks >= min_chunks_per_rank * world_size and heaviest <= (1.0 + max_imbalance) * n_total_blocks / world_size:
+            best_t = t
+            break
+        t -= 1
+    t = best_t
     n_chunks = ceil_div(n_total_blocks, 1 << t)
     ranges = []
     for r in range(world_size):

@@ -1,0 +1,125 @@
+"""GPU tests at sizes the oracle cannot re-hash in seconds: size-independent properties of the commitment
+(sharded == unsharded, tiled host path == resident path, tree of read-back block hashes == root, every sampled path
+reconstructs in two stages), plus the single-GPU emulation of the multi-rank exchange through the C ABI."""
+import importlib
+import random
+
+import pytest
+
+from conftest import PKG
+
+pytestmark = pytest.mark.gpu
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def synthetic(ctx, torch, n_bytes, seed=0xC0DE, first_word=0):
+    d = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    ctx.fill_synthetic_dev(seed, first_word, n_bytes, d.data_ptr())
+    torch.cuda.synchronize()
+    return d
+
+
+def commit_in_ranges(ctx, torch, sharded, d, n_blocks, ranges, top_level):
+    """what N ranks do, run back to back on one GPU: per-range commit, gather of the level-T nodes, replicated top"""
+    shards = []
+    for first, count in ranges:
+        if count == 0:
+            shards.append(None)
+            continue
+        ptr = d.data_ptr() + first * 65536
+        shards.append(sharded.GpuShard(ctx.slot_commit_range_dev(ptr, count * 65536, 2048, 65536, first, n_blocks, top_level)))
+    gathered = torch.cat([s.subtree_roots_tensor() for s in shards if s is not None]).contiguous()
+    assert gathered.numel() == 32 * sharded.level_width(n_blocks, top_level)
+    for s in shards:
+        if s is not None:
+            s.set_top_tensor(gathered)
+    return shards
+
+
+@pytest.mark.parametrize("n_blocks,world", [(16384, 4), (1000, 3), (163, 8), (25 * 64, 8)])
+def test_sharded_commit_equals_whole_commit(ctx, torch_mod, n_blocks, world):
+    torch = torch_mod
+    sharded = importlib.import_module(PKG + ".sharded")
+    d = synthetic(ctx, torch, n_blocks * 65536)
+    with ctx.slot_commit_dev(d.data_ptr(), n_blocks * 65536) as whole:
+        root = whole.root
+        top_level, ranges = sharded.plan_block_ranges(n_blocks, world, max_imbalance=0.05)
+        shards = commit_in_ranges(ctx, torch, sharded, d, n_blocks, ranges, top_level)
+        live = [s for s in shards if s is not None]
+        assert all(s.root == root for s in live)
+        # paths: the owner produces the whole path, everyone else zeros -> the SUM over ranks is the path
+        rnd = random.Random(n_blocks)
+        cells = [rnd.randrange(32 * n_blocks) for _ in range(20)] + [0, 32 * n_blocks - 1]
+        ref_paths, ref_leaves = whole.cell_paths(cells, 32)
+        acc = [[0] * 32 for _ in cells]
+        acc_leaf = [0] * len(cells)
+        for s in live:
+            p, l = s.cell_paths(cells, 32)
+            for i in range(len(cells)):
+                acc[i] = [a + b for a, b in zip(acc[i], p[i])]
+                acc_leaf[i] += l[i]
+        assert acc == ref_paths and acc_leaf == ref_leaves
+        for s in live:
+            s.free()
+
+
+def test_one_gib_slot_properties(ctx, orc, torch_mod):
+    torch = torch_mod
+    n_blocks = 16384
+    d = synthetic(ctx, torch, n_blocks * 65536)
+    with ctx.slot_commit_dev(d.data_ptr(), n_blocks * 65536) as slot:
+        n_cells, nb, bd, sd = slot.shape
+        assert (n_cells, nb, bd, sd) == (524288, 16384, 5, 14)
+        root = slot.root
+        # a checksum of checksums: the tree over the read-back block hashes is the root (GPU tree API and oracle)
+        bh = slot.read_layer(1, 0, 0, n_blocks)
+        assert ctx.merkle_root(bh) == root == orc.merkle_root(bh)
+        # spot-check cell hashes and one block tree against the oracle
+        host = d[: 2 * 65536].cpu().numpy().tobytes()
+        assert slot.read_layer(0, 0, 0, 64) == [orc.hash_bytes(host[i * 2048:(i + 1) * 2048]) for i in range(64)]
+        tail = d[(n_blocks - 1) * 65536:].cpu().numpy().tobytes()
+        assert slot.read_layer(1, 0, n_blocks - 1, 1)[0] == orc.merkle_root([orc.hash_bytes(tail[i * 2048:(i + 1) * 2048]) for i in range(32)])
+        # 100 sampled paths (BASELINE config 5 shape) all reconstruct to the root in two stages (Slot.hs:189-217)
+        idx = ctx.cell_indices(987654321, root, n_cells, 100)
+        assert idx == [orc.cell_index(987654321, root, n_cells, c) for c in range(1, 101)]
+        paths, leaves = slot.cell_paths(idx, 32)
+        for i, p, leaf in zip(idx, paths, leaves):
+            blk = orc.reconstruct_root(leaf, i % 32, 32, p[:5])
+            assert orc.reconstruct_root(blk, i // 32, n_blocks, p[5:19]) == root
+            assert all(v == 0 for v in p[19:])
+    # the tiled host-buffer path (4 x 256 MiB tiles, copy overlapped with the sponge) gives the same root
+    host_all = d.cpu().numpy()
+    with ctx.slot_commit_host(host_all) as slot2:
+        assert slot2.root == root
+
+
+def test_idempotence_and_sensitivity(ctx, torch_mod):
+    torch = torch_mod
+    n = 300 * 65536
+    d = synthetic(ctx, torch, n)
+    with ctx.slot_commit_dev(d.data_ptr(), n) as a, ctx.slot_commit_dev(d.data_ptr(), n) as b:
+        assert a.root == b.root
+        ra = a.root
+    d[n - 1] ^= 1                                                    # flip one bit of the very last byte
+    torch.cuda.synchronize()
+    with ctx.slot_commit_dev(d.data_ptr(), n) as c:
+        assert c.root != ra
+
+
+def test_permutation_batch_2_17_vs_oracle(ctx, orc, torch_mod):
+    """BASELINE config 2 at 2^17 states fully checked (2^20 is timed by tools/first_light.py)"""
+    torch = torch_mod
+    n = 1 << 17
+    a = synthetic(ctx, torch, 96 * n, seed=1)
+    b = torch.empty_like(a)
+    ctx.permutation_batch_dev(a.data_ptr(), b.data_ptr(), n)
+    torch.cuda.synchronize()
+    inp = a.cpu().numpy().tobytes()
+    assert b.cpu().numpy().tobytes() == orc.permutation_batch_bytes(inp)     # inputs are arbitrary 256-bit values: taken mod r

@@ -1,0 +1,149 @@
+"""The N > 1 path on CPU: world_size-2 gloo run of the block-range sharding orchestration
+(codex-storage-proofs-circuits_b200/sharded.py) with an oracle-backed stand-in for the per-rank GPU slot.  What is
+under test is the host logic that is identical on GPUs: range planning, the global odd-node rule at the ragged tail,
+the padded all-gather and compaction of sub-tree roots, the replicated top tree, and owner-only path assembly."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+class OracleShard:
+    """slot-like stand-in: commits blocks [first, first+count) of a fake-data slot with the C oracle, builds levels
+    0..T of the slot tree for that range with the GLOBAL odd-node rule (merkle/bn254.nim:38-53)."""
+
+    def __init__(self, orc, seed, first_block, n_blocks, n_total_blocks, top_level):
+        self.orc, self.first, self.n, self.total, self.T = orc, first_block, n_blocks, n_total_blocks, top_level
+        self.cell_hashes, self.block_trees = [], []
+        for b in range(first_block, first_block + n_blocks):
+            ch = [orc.hash_bytes(orc.gen_fake_cell(seed, 32 * b + c, 2048)) for c in range(32)]
+            self.cell_hashes += ch
+            self.block_trees.append(orc.merkle_layers(ch))
+        self.low = [[t[-1][0] for t in self.block_trees]]
+        for l in range(top_level):
+            cur, nxt = self.low[l], []
+            for i in range((len(cur) + 1) // 2):
+                key = 1 if l == 0 else 0
+                if 2 * i + 1 < len(cur):
+                    nxt.append(orc.compress(cur[2 * i], cur[2 * i + 1], key))
+                else:
+                    nxt.append(orc.compress(cur[2 * i], 0, key + 2))
+            self.low.append(nxt)
+        self.top = None
+
+    def subtree_roots_tensor(self, device="cpu"):
+        raw = b"".join(int(v).to_bytes(32, "little") for v in self.low[self.T])
+        return torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+
+    def set_top_tensor(self, t):
+        raw = bytes(t.numpy())
+        nodes = [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
+        self.top = self.orc.merkle_layers(nodes, bottom=(self.T == 0))
+
+    @property
+    def root(self):
+        return self.top[-1][0]
+
+    def cell_paths(self, indices, max_depth):
+        paths, leaves = [], []
+        for ci in indices:
+            b = ci // 32
+            if not (self.first <= b < self.first + self.n):
+                paths.append([0] * max_depth)
+                leaves.append(0)
+                continue
+            lb = b - self.first
+            path, k = [], ci % 32
+            for l in range(5):
+                path.append(self.block_trees[lb][l][k ^ 1])
+                k >>= 1
+            node, width = b, self.total
+            n_levels = (len(self.top) - 1) + self.T
+            for l in range(n_levels):
+                sib = node ^ 1
+                if sib >= width:
+                    path.append(0)
+                elif l < self.T:
+                    path.append(self.low[l][sib - (self.first >> l)])
+                else:
+                    path.append(self.top[l - self.T][sib])
+                node >>= 1
+                width = (width + 1) // 2
+            paths.append(path + [0] * (max_depth - len(path)))
+            leaves.append(self.cell_hashes[32 * lb + ci % 32])
+        return paths, leaves
+
+
+def _worker(rank, world, port, n_total_blocks, seed, out_q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sharded = importlib.import_module(PKG + ".sharded")
+        from oracle import coracle as orc
+        top_level, ranges = sharded.plan_block_ranges(n_total_blocks, world, max_imbalance=0.35)
+        first, count = ranges[rank]
+        shard = OracleShard(orc, seed, first, count, n_total_blocks, top_level)
+        sharded.exchange_subtree_roots(shard, n_total_blocks, top_level, ranges, device="cpu")
+        indices = [0, 31, 32 * (n_total_blocks // 2), 32 * n_total_blocks - 1, 32 * (n_total_blocks - 1)]
+        paths, leaves = sharded.gather_cell_paths(shard, indices, 16, device="cpu")
+        out_q.put((rank, top_level, ranges, shard.root, indices, paths, leaves))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total_blocks", [13, 16, 21])
+def test_two_rank_sharded_commit_matches_single_process(orc, n_total_blocks):
+    seed, world = 777, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + n_total_blocks
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total_blocks, seed, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    root, bh, ch = orc.commit_fake_slot(seed, 32 * n_total_blocks, want_cells=True)
+    big = orc.merkle_layers(bh)
+    depth = len(big) - 1
+    for rank, top_level, ranges, r_root, indices, paths, leaves in results:
+        assert sum(c for _, c in ranges) == n_total_blocks and ranges[0][0] == 0
+        assert all(f % (1 << top_level) == 0 for f, c in ranges if c)
+        assert r_root == root, f"rank {rank}: sharded root differs from the single-process root"
+        for ci, path, leaf in zip(indices, paths, leaves):
+            assert leaf == ch[ci]
+            blk = orc.reconstruct_root(leaf, ci % 32, 32, path[:5])
+            assert blk == bh[ci // 32]
+            assert orc.reconstruct_root(blk, ci // 32, n_total_blocks, path[5:5 + depth]) == root
+            assert all(v == 0 for v in path[5 + depth:])
+
+
+def test_range_planning_properties(pkg):
+    sharded = importlib.import_module(PKG + ".sharded")
+    for n_blocks, world in [(1638400, 8), (163840, 1), (163840, 3), (5, 8), (1, 2), (2097152, 8), (1000, 7)]:
+        t, ranges = sharded.plan_block_ranges(n_blocks, world)
+        assert len(ranges) == world and sum(c for _, c in ranges) == n_blocks
+        pos = 0
+        for f, c in ranges:
+            assert f == pos or c == 0
+            if c:
+                assert f % (1 << t) == 0 and (c % (1 << t) == 0 or f + c == n_blocks)
+            pos += c
+        counts = [c for _, c in ranges]
+        if n_blocks >= 64 * world:
+            assert max(counts) <= 1.01 * n_blocks / world + 1          # the most loaded rank is within 1 % of ideal
+    t, ranges = sharded.plan_block_ranges(1638400, 8)              # BASELINE config 4: 100 GiB over 8 GPUs
+    assert t == 13 and all(c == 204800 for _, c in ranges)         # 25 chunks of 8192 blocks per GPU
+    t, ranges = sharded.fixed_ranges(163840, 8)                    # bench.py weak-scaling layout
+    assert t == 15 and ranges[3] == (3 * 163840, 163840)
+    assert sharded.level_width(163840, 15) == 5 and sharded.level_width(5, 3) == 1
