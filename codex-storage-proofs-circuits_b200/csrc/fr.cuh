@@ -28,9 +28,15 @@
 #if defined(__CUDACC__)
 #define CDX_HD __host__ __device__ __forceinline__
 #define CDX_D __device__ __forceinline__
+#ifdef CDX_MODMUL_NOINLINE
+#define CDX_MM __device__ __noinline__
+#else
+#define CDX_MM __device__ __forceinline__
+#endif
 #else
 #define CDX_HD inline
 #define CDX_D inline
+#define CDX_MM inline
 #endif
 
 namespace cdx {
@@ -99,6 +105,9 @@ CDX_D void mont_row_next(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t b
 }
 
 // Reduction row: m = e[0] * (-r^-1) mod 2^32; (e,o) += m*r, which clears e[0].  The modulus limbs are immediates.
+// (Tried and rejected, see DESIGN.md: computing m and the r0 column with shifts/adds instead of two multiplies --
+// ptxas moves the extra adds onto the FMA pipe as IMAD.X/IMAD.IADD and the longer dependency chain costs more than
+// the two multiply slots save: 14.3 vs 15.8 GB/s.)
 CDX_D void mont_row_redc(uint32_t* e, uint32_t* o) {
   uint32_t m = e[0] * CDX_NP;
   asm("{\n\t"
@@ -117,6 +126,44 @@ CDX_D void mont_row_redc(uint32_t* e, uint32_t* o) {
       : "r"(m), "n"(CDX_N1), "n"(CDX_N0), "n"(CDX_N3), "n"(CDX_N2), "n"(CDX_N5), "n"(CDX_N4), "n"(CDX_N7),
         "n"(CDX_N6));
 }
+
+// Reduction-only iteration (used by the squaring, which reduces a finished 512-bit product): the same as
+// mont_row_next followed by mont_row_redc with no product row in between.  On entry e is the even-aligned window
+// (positions 0..7), o the previous window after its divide by 2^32 (o[k] at position k-1, o[0] dead).  On exit o is
+// the new odd-aligned accumulator (positions 1..8) and e the even one with its low limb cancelled.
+CDX_D void mont_row_redc_shift(uint32_t* e, uint32_t* o) {
+  const uint32_t m = (e[0] + o[1]) * CDX_NP;          // from the true low limb of the window
+  asm("{\n\t"
+      "add.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %8, %17, %16, %10;  madc.hi.cc.u32 %9, %17, %16, %11;\n\t"
+      "madc.lo.cc.u32 %10, %19, %16, %12; madc.hi.cc.u32 %11, %19, %16, %13;\n\t"
+      "madc.lo.cc.u32 %12, %21, %16, %14; madc.hi.cc.u32 %13, %21, %16, %15;\n\t"
+      "madc.lo.cc.u32 %14, %23, %16, 0;   madc.hi.u32 %15, %23, %16, 0;\n\t"
+      "mad.lo.cc.u32 %0, %18, %16, %0;  madc.hi.cc.u32 %1, %18, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %20, %16, %2; madc.hi.cc.u32 %3, %20, %16, %3;\n\t"
+      "madc.lo.cc.u32 %4, %22, %16, %4; madc.hi.cc.u32 %5, %22, %16, %5;\n\t"
+      "madc.lo.cc.u32 %6, %24, %16, %6; madc.hi.cc.u32 %7, %24, %16, %7;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      "}"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(m), "n"(CDX_N1), "n"(CDX_N0), "n"(CDX_N3), "n"(CDX_N2), "n"(CDX_N5), "n"(CDX_N4), "n"(CDX_N7),
+        "n"(CDX_N6));
+}
+
+// Carry-flag building blocks for the squaring's product rows.  Each is one asm statement; the PTX condition code
+// carries from one to the next (compiler-generated PTX never writes CC, and `volatile` keeps the order).
+CDX_D void cc_mad_first(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {   // (hi:lo) += a*b, carry out
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+CDX_D void cc_mad_next(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {    // carry in and out
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+CDX_D void cc_carry_into(uint32_t& x) { asm volatile("addc.u32 %0, %0, 0;" : "+r"(x)); }                 // x += carry
+CDX_D void cc_add_first(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+CDX_D void cc_add_next(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+CDX_D void cc_add_last(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+CDX_D uint32_t shl1_funnel(uint32_t lo, uint32_t hi) { return __funnelshift_l(lo, hi, 1); }              // (hi:lo << 1) >> 32
 
 // r = e + (o >> 32 limbs aligned as after a row): r[k] = e[k] + o[k+1] with carry
 CDX_D void mont_merge(uint32_t* r, const uint32_t* e, const uint32_t* o) {
@@ -160,6 +207,14 @@ namespace cdx {
 void mont_row_first(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
 void mont_row_next(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
 void mont_row_redc(uint32_t*, uint32_t*);
+void mont_row_redc_shift(uint32_t*, uint32_t*);
+void cc_mad_first(uint32_t&, uint32_t&, uint32_t, uint32_t);
+void cc_mad_next(uint32_t&, uint32_t&, uint32_t, uint32_t);
+void cc_carry_into(uint32_t&);
+void cc_add_first(uint32_t&, uint32_t, uint32_t);
+void cc_add_next(uint32_t&, uint32_t, uint32_t);
+void cc_add_last(uint32_t&, uint32_t, uint32_t);
+uint32_t shl1_funnel(uint32_t, uint32_t);
 void mont_merge(uint32_t*, const uint32_t*, const uint32_t*);
 void add256(uint32_t*, const uint32_t*, const uint32_t*);
 uint32_t sub_modulus(uint32_t*, const uint32_t*);
@@ -187,7 +242,84 @@ CDX_D Fr mont_mul(const Fr& a, const Fr& b) {
   return r;
 }
 
+// a*a*2^-256 mod r with 36 instead of 64 operand products (2/3 of all multiplications on this path are squarings:
+// x^2 and x^4 of every S-box).  a < 2r; result < a^2/2^256 + r < 2r, same contract as mont_mul.
+//   1. cross products a_i*a_j (i < j), 28 of them, row by row into an even- and an odd-aligned 512-bit accumulator
+//      (a chain never has to ripple: the limb above its last pair has only ever received carries);
+//   2. T = 2*(E + O) + sum a_i^2 * 2^(64 i): one add chain, one funnel-shift pass, one 8-product carry chain;
+//   3. Montgomery-reduce the low half with 8 reduction-only rows, add the high half (< 0.76 r, no overflow).
+#ifdef CDX_NO_DEDICATED_SQR
 CDX_D Fr mont_sqr(const Fr& a) { return mont_mul(a, a); }
+#else
+CDX_D Fr mont_sqr(const Fr& a) {
+  uint32_t E[16], O[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) E[k] = O[k] = 0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    {  // products landing on even positions i+j
+      bool first = true;
+      int last = -1;
+#pragma unroll
+      for (int j = i + 1; j < 8; ++j) {
+        if (((i + j) & 1) == 0) {
+          if (first) cc_mad_first(E[i + j], E[i + j + 1], a.l[i], a.l[j]);
+          else cc_mad_next(E[i + j], E[i + j + 1], a.l[i], a.l[j]);
+          first = false;
+          last = i + j;
+        }
+      }
+      if (!first) cc_carry_into(E[last + 2]);
+    }
+    {  // products landing on odd positions
+      bool first = true;
+      int last = -1;
+#pragma unroll
+      for (int j = i + 1; j < 8; ++j) {
+        if (((i + j) & 1) == 1) {
+          if (first) cc_mad_first(O[i + j], O[i + j + 1], a.l[i], a.l[j]);
+          else cc_mad_next(O[i + j], O[i + j + 1], a.l[i], a.l[j]);
+          first = false;
+          last = i + j;
+        }
+      }
+      if (!first) cc_carry_into(O[last + 2]);
+    }
+  }
+  // S = E + O (positions 1..15), then T = 2S
+  uint32_t S[16], T[16];
+  S[0] = 0;
+  cc_add_first(S[1], E[1], O[1]);
+#pragma unroll
+  for (int k = 2; k < 15; ++k) cc_add_next(S[k], E[k], O[k]);
+  cc_add_last(S[15], E[15], O[15]);
+  T[0] = 0;
+#pragma unroll
+  for (int k = 1; k < 16; ++k) T[k] = shl1_funnel(S[k - 1], S[k]);
+  // + diagonal squares, one carry chain over all 16 limbs
+  cc_mad_first(T[0], T[1], a.l[0], a.l[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) cc_mad_next(T[2 * i], T[2 * i + 1], a.l[i], a.l[i]);
+  // reduce the low half
+  uint32_t e[8], o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    e[k] = T[k];
+    o[k] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    mont_row_redc_shift(e, o);
+    mont_row_redc_shift(o, e);
+  }
+  Fr u, hi, r;
+  mont_merge(u.l, e, o);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) hi.l[k] = T[8 + k];
+  add256(r.l, u.l, hi.l);
+  return r;
+}
+#endif
 
 // [0, 2r) -> [0, r)
 CDX_D Fr reduce_once(const Fr& a) {

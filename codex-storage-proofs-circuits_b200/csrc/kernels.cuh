@@ -194,29 +194,28 @@ __global__ void k_fill_synthetic(uint64_t seed, uint64_t first_word, size_t n_wo
   }
 }
 
-// Roofline probe: dependency-light integer multiply streams, ILP 8 per thread.
-//   kind 0: IMAD.WIDE.U32 (64-bit accumulate)   kind 1: IMAD.WIDE.U32.X carry chains of 4 (as in the
-//   Montgomery rows)   kind 2: 32-bit IMAD
+// Roofline probe: integer multiply streams, ILP 8 per thread, SASS verified (see tools/probes/probe_pipes.cu).
+//   kind 0: IMAD.WIDE.U32 Rd, Ra, Rb, RZ (no carry)   kind 1: IMAD.WIDE.U32.X carry chains of 4 (exactly the
+//   form of the Montgomery rows)   kind 2: 32-bit IMAD
+// On B200 kinds 0 and 1 run at about half the rate of kind 2: a 32x32->64 product costs two FMA-heavy slots.
 #define CDX_PROBE_OPS_PER_ITER 32
 __global__ void k_probe_imad(int kind, uint32_t iters, uint32_t seed, uint32_t* __restrict__ sink) {
   uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
   uint32_t r0 = a, r1 = b, r2 = a ^ b, r3 = a + b, r4 = a * 3, r5 = b * 5, r6 = a * 7, r7 = b * 9;
   uint32_t s0 = 1, s1 = 2, s2 = 3, s3 = 4, s4 = 5, s5 = 6, s6 = 7, s7 = 8;
   if (kind == 0) {
+    // (lo,hi) = r_i * b ; r_i = lo ^ hi : each product feeds the next multiplicand, so ptxas can neither hoist the
+    // multiply nor re-associate an accumulation into IADD3 chains (it does both to `acc += a*b`)
     for (uint32_t it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        asm volatile(
-            "{\n\t.reg .u64 t0,t1,t2,t3,t4,t5,t6,t7;\n\t"
-            "mov.b64 t0,{%0,%8}; mov.b64 t1,{%1,%9}; mov.b64 t2,{%2,%10}; mov.b64 t3,{%3,%11};\n\t"
-            "mov.b64 t4,{%4,%12}; mov.b64 t5,{%5,%13}; mov.b64 t6,{%6,%14}; mov.b64 t7,{%7,%15};\n\t"
-            "mad.wide.u32 t0,%16,%17,t0; mad.wide.u32 t1,%16,%17,t1; mad.wide.u32 t2,%16,%17,t2; mad.wide.u32 t3,%16,%17,t3;\n\t"
-            "mad.wide.u32 t4,%16,%17,t4; mad.wide.u32 t5,%16,%17,t5; mad.wide.u32 t6,%16,%17,t6; mad.wide.u32 t7,%16,%17,t7;\n\t"
-            "mov.b64 {%0,%8},t0; mov.b64 {%1,%9},t1; mov.b64 {%2,%10},t2; mov.b64 {%3,%11},t3;\n\t"
-            "mov.b64 {%4,%12},t4; mov.b64 {%5,%13},t5; mov.b64 {%6,%14},t6; mov.b64 {%7,%15},t7;\n\t}"
-            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(s0), "+r"(s1), "+r"(s2),
-              "+r"(s3), "+r"(s4), "+r"(s5), "+r"(s6), "+r"(s7)
-            : "r"(a), "r"(b));
+      for (int u = 0; u < 4; ++u) {
+        uint64_t p0 = (uint64_t)r0 * b, p1 = (uint64_t)r1 * b, p2 = (uint64_t)r2 * b, p3 = (uint64_t)r3 * b;
+        uint64_t p4 = (uint64_t)r4 * b, p5 = (uint64_t)r5 * b, p6 = (uint64_t)r6 * b, p7 = (uint64_t)r7 * b;
+        r0 = (uint32_t)p0 ^ (uint32_t)(p0 >> 32); r1 = (uint32_t)p1 ^ (uint32_t)(p1 >> 32);
+        r2 = (uint32_t)p2 ^ (uint32_t)(p2 >> 32); r3 = (uint32_t)p3 ^ (uint32_t)(p3 >> 32);
+        r4 = (uint32_t)p4 ^ (uint32_t)(p4 >> 32); r5 = (uint32_t)p5 ^ (uint32_t)(p5 >> 32);
+        r6 = (uint32_t)p6 ^ (uint32_t)(p6 >> 32); r7 = (uint32_t)p7 ^ (uint32_t)(p7 >> 32);
+      }
     }
   } else if (kind == 1) {
     for (uint32_t it = 0; it < iters; ++it) {

@@ -49,31 +49,38 @@ CDX_D void mix_external(Fr& x, Fr& y, Fr& z) {
   z = add_mod(z, s);
 }
 
-CDX_D void external_round(int r, Fr& x, Fr& y, Fr& z) {            // Permutation.hs:28-33
-  x = sbox(add_lazy(x, CDX_RC(3 * r + 0)));
-  y = sbox(add_lazy(y, CDX_RC(3 * r + 1)));
-  z = sbox(add_lazy(z, CDX_RC(3 * r + 2)));
-  mix_external(x, y, z);
-}
-
-CDX_D void internal_round(int r, Fr& x, Fr& y, Fr& z) {            // Permutation.hs:19-26, matrix [[2,1,1],[1,2,1],[1,1,3]]
-  Fr xs = sbox(add_lazy(x, CDX_RC(24 + r)));
-  Fr s = add_mod(add_mod(xs, y), z);
-  x = add_mod(xs, s);
+// internal-round mix with x already through its S-box            Permutation.hs:19-26, matrix [[2,1,1],[1,2,1],[1,1,3]]
+CDX_D void mix_internal(Fr& x, Fr& y, Fr& z) {
+  Fr s = add_mod(add_mod(x, y), z);
+  x = add_mod(x, s);
   y = add_mod(y, s);
   z = add_mod(dbl_mod(z), s);
 }
 
 // state words < r in, < r out                                       Permutation.hs:40-45
+// Two S-box instances in the instruction stream: one in the internal-round loop (56 of the 80 S-box evaluations,
+// nothing else in its body), one shared by all eight external rounds, which run it three times while rotating the
+// state words through the x slot (24 register moves per use).  Inlining three S-boxes per external round made that
+// loop 35 KB of SASS, beyond the instruction cache.
 CDX_D void permute(Fr& x, Fr& y, Fr& z) {
   mix_external(x, y, z);
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) external_round(4 * half + r, x, y, z);
+    for (int i = 0; i < 12; ++i) {       // 4 external rounds x 3 words
+      x = sbox(add_lazy(x, CDX_RC(12 * half + i)));
+      const Fr t = x;                    // rotate: the next word moves into the x slot
+      x = y;
+      y = z;
+      z = t;
+      if (i % 3 == 2) mix_external(x, y, z);
+    }
     if (half == 0) {
 #pragma unroll 1
-      for (int r = 0; r < 56; ++r) internal_round(r, x, y, z);
+      for (int r = 0; r < 56; ++r) {
+        x = sbox(add_lazy(x, CDX_RC(24 + r)));
+        mix_internal(x, y, z);
+      }
     }
   }
 }

@@ -169,9 +169,9 @@ int cdx_fill_synthetic_dev(cdx_ctx* ctx, uint64_t seed, uint64_t first_word, siz
 
 /* ---- measurement ---------------------------------------------------------------------------------------- */
 
-/* Integer-multiply roofline probe: runs a dependency-free IMAD.WIDE.U32 loop on every SM and returns the
- * achieved rate in instructions (thread-level, i.e. 32 per warp instruction) per second.  kind 0 = IMAD.WIDE.U32,
- * 1 = IMAD.WIDE.U32.X carry chains as in the Montgomery rows, 2 = 32-bit IMAD. */
+/* Integer-multiply roofline probe: runs a multiply stream with ILP 8 on every SM and returns the achieved rate in
+ * thread-level instructions per second.  kind 0 = IMAD.WIDE.U32 without carry (each product feeds the next
+ * multiplicand), 1 = IMAD.WIDE.U32.X carry chains as in the Montgomery rows, 2 = 32-bit IMAD. */
 int cdx_probe_imad_rate(cdx_ctx* ctx, int kind, double* ops_per_second, double* elapsed_ms);
 
 #ifdef __cplusplus

@@ -59,6 +59,36 @@ inline void mont_row_redc(uint32_t* e, uint32_t* o) {
   o[7] = c.addc(o[7], 0);
 }
 
+inline void mont_row_redc_shift(uint32_t* e, uint32_t* o) {
+  const uint32_t* n = kModHost;
+  const uint32_t m = (e[0] + o[1]) * CDX_NP;
+  emul::CC c;
+  e[0] = c.add_cc(e[0], o[1]);
+  o[0] = c.madc_lo_cc(n[1], m, o[2]); o[1] = c.madc_hi_cc(n[1], m, o[3]);
+  o[2] = c.madc_lo_cc(n[3], m, o[4]); o[3] = c.madc_hi_cc(n[3], m, o[5]);
+  o[4] = c.madc_lo_cc(n[5], m, o[6]); o[5] = c.madc_hi_cc(n[5], m, o[7]);
+  o[6] = c.madc_lo_cc(n[7], m, 0);    o[7] = c.madc_hi(n[7], m, 0);
+  e[0] = c.mad_lo_cc(n[0], m, e[0]);  e[1] = c.madc_hi_cc(n[0], m, e[1]);
+  e[2] = c.madc_lo_cc(n[2], m, e[2]); e[3] = c.madc_hi_cc(n[2], m, e[3]);
+  e[4] = c.madc_lo_cc(n[4], m, e[4]); e[5] = c.madc_hi_cc(n[4], m, e[5]);
+  e[6] = c.madc_lo_cc(n[6], m, e[6]); e[7] = c.madc_hi_cc(n[6], m, e[7]);
+  o[7] = c.addc(o[7], 0);
+}
+
+// statement-level primitives: the PTX condition code lives across asm statements; here it is a thread-local flag
+static thread_local emul::CC g_cc;
+inline void cc_mad_first(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = g_cc.mad_lo_cc(a, b, lo); hi = g_cc.madc_hi_cc(a, b, hi); }
+inline void cc_mad_next(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = g_cc.madc_lo_cc(a, b, lo); hi = g_cc.madc_hi_cc(a, b, hi); }
+inline void cc_carry_into(uint32_t& x) {
+  const uint64_t s = (uint64_t)x + g_cc.cf;
+  if (s >> 32) __builtin_trap();   // a chain end must never overflow its carry limb (the device code cannot see this)
+  x = (uint32_t)s;
+}
+inline void cc_add_first(uint32_t& r, uint32_t a, uint32_t b) { r = g_cc.add_cc(a, b); }
+inline void cc_add_next(uint32_t& r, uint32_t a, uint32_t b) { r = g_cc.addc_cc(a, b); }
+inline void cc_add_last(uint32_t& r, uint32_t a, uint32_t b) { r = g_cc.addc(a, b); }
+inline uint32_t shl1_funnel(uint32_t lo, uint32_t hi) { return (hi << 1) | (lo >> 31); }
+
 inline void mont_merge(uint32_t* r, const uint32_t* e, const uint32_t* o) {
   emul::CC c;
   r[0] = c.add_cc(e[0], o[1]);

@@ -13,6 +13,7 @@ static void store(uint8_t* p, const Fr& a) { memcpy(p, a.l, 32); }
 extern "C" {
 // raw Montgomery product of two 256-bit values (no conversion): out = a*b*2^-256 mod r, lazily reduced
 void emul_mont_mul_raw(const uint8_t* a, const uint8_t* b, uint8_t* out) { store(out, mont_mul(load(a), load(b))); }
+void emul_mont_sqr_raw(const uint8_t* a, uint8_t* out) { store(out, mont_sqr(load(a))); }
 void emul_to_mont(const uint8_t* a, uint8_t* out) { store(out, to_mont(load(a))); }
 void emul_from_mont(const uint8_t* a, uint8_t* out) { store(out, from_mont(load(a))); }
 void emul_add_mod(const uint8_t* a, const uint8_t* b, uint8_t* out) { store(out, add_mod(load(a), load(b))); }

@@ -41,6 +41,22 @@ def test_mont_mul_lazy_bounds(emul):
             assert v < 2 * R
 
 
+def test_mont_sqr_dedicated(emul):
+    """36-product squaring + reduction-only rows: same contract as mont_mul(a, a)"""
+    rnd = random.Random(17)
+    rinv = pow(1 << 256, -1, R)
+    out, out2 = C.create_string_buffer(32), C.create_string_buffer(32)
+    cases = [rnd.randrange(2 * R) for _ in range(3000)] + [0, 1, R, R - 1, 2 * R - 1, (1 << 254) - 1, 0xffffffff, (1 << 254) - (1 << 32)]
+    cases += [int("ffffffff" * k + "00000000" * (7 - k) + "ffffffff", 16) % (2 * R) for k in range(7)]
+    for a in cases:
+        emul.emul_mont_sqr_raw(f2b(a), out)
+        v = b2f(out.raw)
+        assert v % R == a * a * rinv % R, hex(a)
+        assert v <= (a * a >> 256) + R and v < 2 * R
+        emul.emul_mont_mul_raw(f2b(a), f2b(a), out2)
+        assert b2f(out2.raw) % R == v % R
+
+
 def test_permutation_and_compress(emul, orc):
     rnd = random.Random(8)
     out = C.create_string_buffer(96)
