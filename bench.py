@@ -13,8 +13,8 @@ block tree, the slot tree, and the 32-byte root read back.  Workload at N = 1: B
   value     whole-job GB/s with the slot bytes already resident in HBM (CUDA events, max over ranks)
   e2e       the same through the host-buffer C-ABI call (pinned host slot -> cdx_slot_commit[_range]_host), H2D of
             every byte inside the timed region, root read back
-  roofline  the dominant kernel (k_hash_cells) timed alone with CUDA events; bound = FMA-pipe integer multiply
-            issue (DESIGN.md "Roofline"), peak = IMAD.WIDE.U32 rate measured by a probe kernel in the same run;
+  roofline  the dominant kernel (k_hash_cells) timed alone with CUDA events; bound = FMA-heavy-pipe integer multiply
+            issue (DESIGN.md "Roofline"), peak = best IMAD.WIDE.U32 rate measured by probe kernels in the same run;
             an `hbm` sub-object shows HBM is three orders of magnitude from binding
   cpu_baseline  oracle (C restatement of the reference path; the Nim toolchain is absent) on a bounded sample
 """
@@ -276,8 +276,10 @@ def main() -> None:
     k_ev, _, _ = timed(lambda: ctx.hash_cells_dev(d_slot.data_ptr(), n_cells, CELL, d_hashes.data_ptr()), args.steps)
     k_ms = 1e3 * k_ev / args.steps
     del d_hashes
-    imad_wide, _ = ctx.probe_imad_rate(0)
-    imad_wide_x, _ = ctx.probe_imad_rate(1)
+    imad_wide_rz, _ = ctx.probe_imad_rate(0)        # IMAD.WIDE.U32 Rd,Ra,Rb,RZ (no carry), product fed back into the multiplicand
+    imad_wide_x, _ = ctx.probe_imad_rate(1)         # IMAD.WIDE.U32.X carry chains, the form the Montgomery rows use
+    imad32, _ = ctx.probe_imad_rate(2)              # 32-bit IMAD, for context: twice the rate of any 32x32->64 form
+    imad_wide = max(imad_wide_rz, imad_wide_x)
     kernel_imads = n_cells * 34 * MODMUL_PER_PERM * IMAD_PER_MODMUL
     achieved = kernel_imads / (k_ms * 1e-3)
     hbm_peak = None
@@ -288,10 +290,13 @@ def main() -> None:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = n_cells * (CELL + 32)
     roofline = {
-        "kernel": "k_hash_cells", "bound": "int32_imad (FMA-pipe IMAD.WIDE.U32 issue; neither hbm nor tensor)",
+        "kernel": "k_hash_cells", "bound": "int32_imad (FMA-heavy pipe: IMAD.WIDE.U32 issue; neither hbm nor tensor)",
         "achieved": achieved / 1e12, "peak": imad_wide / 1e12, "unit": "T int-multiply instr/s", "frac": achieved / imad_wide,
-        "peak_source": "IMAD.WIDE.U32 probe kernel measured in this run (cdx_probe_imad_rate kind 0)",
-        "peak_carry_chain": imad_wide_x / 1e12, "frac_of_carry_chain_peak": achieved / imad_wide_x,
+        "peak_source": "best IMAD.WIDE.U32 rate measured in this run by cdx_probe_imad_rate (max of the no-carry and the carry-chain form); "
+                       "MEASURED_PEAKS.json has no integer peak",
+        "note": "achieved = 136 multiply instructions (schoolbook 8x32-bit CIOS) x 240 modmuls x 34 perms x cells / kernel time; the kernel "
+                "executes fewer (dedicated 36-product squaring), so frac can exceed 1 -- SURVEY.md 8d: no credit in the denominator",
+        "probe_rates_T_per_s": {"imad_wide_u32_no_carry": imad_wide_rz / 1e12, "imad_wide_u32_x_carry_chain": imad_wide_x / 1e12, "imad_u32": imad32 / 1e12},
         "kernel_ms": k_ms, "algorithmic_imads_per_launch": kernel_imads, "modmuls_per_s": achieved / IMAD_PER_MODMUL,
         "traffic": None,
         "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,

@@ -22,6 +22,8 @@ struct cdx_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging for *_host entry points
+  cudaStream_t stream2 = nullptr;      // second compute stream: odd tiles of a host-resident slot (kernels overlap at the tile seams)
+  cudaEvent_t ev_join = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
   void* d_stage[2] = {nullptr, nullptr};
@@ -112,6 +114,8 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
@@ -134,6 +138,8 @@ extern "C" void cdx_ctx_destroy(cdx_ctx* ctx) {
   }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 
@@ -547,19 +553,27 @@ static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   if (rc) return rc;
   const size_t cpb = block_size / cell_size;
   auto body = [&]() -> int {
+    // tile t lives in staging buffer t&1 and is hashed on compute stream t&1, so the cell kernels of consecutive
+    // tiles overlap at the seams (the tail of one fills up with the head of the next) while each buffer is still
+    // reused strictly in order: copy(t) waits for hash(t-2), hash(t) waits for copy(t).
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));              // the slot's buffers were allocated on stream
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
     size_t done = 0;
     for (int t = 0; done < n_blocks; ++t) {
       const int b = t & 1;
+      cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
       const size_t nb = n_blocks - done < tile_blocks ? n_blocks - done : tile_blocks;
       if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
       CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, ctx->copy_stream));
       CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-      CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-      LAUNCH(ctx, k_hash_cells, nb * cpb, ctx->stream, (const uint32_t*)ctx->d_stage[b], nb * cpb, (uint32_t)(cell_size / 4),
+      CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
+      LAUNCH(ctx, k_hash_cells, nb * cpb, cs, (const uint32_t*)ctx->d_stage[b], nb * cpb, (uint32_t)(cell_size / 4),
              s->forest[0] + 32 * done * cpb);
-      CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], cs));
       done += nb;
     }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));             // trees run on stream after both tile streams
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     int r = build_local_trees(s);
     if (r) return r;
     if (whole_slot) {
@@ -572,6 +586,7 @@ static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   rc = body();
   if (rc) {
     cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream2);
     cudaStreamSynchronize(ctx->stream);
     cdx_slot_free(s);
     return rc;

@@ -8,8 +8,14 @@
 // IMAD.WIDE.U32(.X) with the carry chain riding on the predicate carry: products of even limbs accumulate in
 // an "even" 256-bit accumulator (64-bit slots at limb positions 0,2,4,6) and products of odd limbs in an "odd"
 // one (slots at 1,3,5,7); dividing by 2^32 after each row swaps their roles, so no product ever has to be
-// re-aligned.  Cost per product: 128 IMAD.WIDE.U32 + 8 IMAD (the 2n^2+n of BASELINE.md section 2) and ~30
-// IADD3 on the ALU pipe.
+// re-aligned.  Cost per product: 120 IMAD.WIDE.U32[.X] + 8 IMAD.HI + 8 IMAD (the 2n^2+n = 136 of BASELINE.md
+// section 2) and ~30 IADD3 on the ALU pipe.  Squaring (2/3 of all multiplications on this path) has its own
+// routine with 36 instead of 64 operand products.
+//
+// What bounds it (measured, tools/probes/probe_pipes.cu): integer multiplies issue only on the FMA-heavy pipe;
+// a 32-bit IMAD runs at 61-63 lanes/clk/SM, every form that produces the high half of the product (IMAD.HI,
+// IMAD.WIDE with or without carry) at 25-32: a 32x32->64 product costs two pipe slots whatever form it takes, so
+// the only lever left is the number of products.
 //
 // Range discipline ("units of r", r < 2^254 so 2^256 > 5.29 r):
 //   mont_mul(a,b) needs a < 4.29 r (= 2^256 - r: the running row sum is < a + r and must fit 256 bits),
@@ -105,9 +111,9 @@ CDX_D void mont_row_next(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t b
 }
 
 // Reduction row: m = e[0] * (-r^-1) mod 2^32; (e,o) += m*r, which clears e[0].  The modulus limbs are immediates.
-// (Tried and rejected, see DESIGN.md: computing m and the r0 column with shifts/adds instead of two multiplies --
-// ptxas moves the extra adds onto the FMA pipe as IMAD.X/IMAD.IADD and the longer dependency chain costs more than
-// the two multiply slots save: 14.3 vs 15.8 GB/s.)
+// (Tried and rejected, see DESIGN.md section 4: r0 = 2^32 - 2^28 + 1 and -r^-1 = -(2^28 + 1) allow m and the r0 column
+// to be computed with shifts/adds instead of two multiplies, but ptxas moves the extra adds onto the FMA pipe as
+// IMAD.X / IMAD.IADD and the dependency chain gets longer: 16.0 vs 17.0 GB/s on the cell kernel.)
 CDX_D void mont_row_redc(uint32_t* e, uint32_t* o) {
   uint32_t m = e[0] * CDX_NP;
   asm("{\n\t"
@@ -248,9 +254,6 @@ CDX_D Fr mont_mul(const Fr& a, const Fr& b) {
 //      (a chain never has to ripple: the limb above its last pair has only ever received carries);
 //   2. T = 2*(E + O) + sum a_i^2 * 2^(64 i): one add chain, one funnel-shift pass, one 8-product carry chain;
 //   3. Montgomery-reduce the low half with 8 reduction-only rows, add the high half (< 0.76 r, no overflow).
-#ifdef CDX_NO_DEDICATED_SQR
-CDX_D Fr mont_sqr(const Fr& a) { return mont_mul(a, a); }
-#else
 CDX_D Fr mont_sqr(const Fr& a) {
   uint32_t E[16], O[16];
 #pragma unroll
@@ -319,7 +322,6 @@ CDX_D Fr mont_sqr(const Fr& a) {
   add256(r.l, u.l, hi.l);
   return r;
 }
-#endif
 
 // [0, 2r) -> [0, r)
 CDX_D Fr reduce_once(const Fr& a) {
