@@ -188,6 +188,11 @@ def main() -> None:
     if args.impl == "reference":
         return run_reference(args)
 
+    # only the JSON line may reach stdout: library chatter (e.g. "NCCL version ..." printed at communicator creation)
+    # is sent to stderr for the duration of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module(PKG)
@@ -370,7 +375,10 @@ def main() -> None:
             "slot_root": hex(root), "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
