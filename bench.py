@@ -180,6 +180,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slot-gib", type=float, default=10.0, help="GiB of slot data per GPU (default: BASELINE config 3, 10 GiB)")
+    ap.add_argument("--total-gib", type=float, default=0.0,
+                    help="strong scaling: ONE slot of this many GiB split over the ranks by plan_block_ranges (BASELINE config 4: 100); "
+                         "overrides --slot-gib")
     ap.add_argument("--ref-sample-mib", type=int, default=64, help="bytes per step of the --impl reference CPU run")
     ap.add_argument("--cpu-sample-mib", type=int, default=256, help="sample committed once for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -208,11 +211,17 @@ def main() -> None:
     ctx = pkg.Context(local_rank)                      # raises if libcodexcommit.so or the GPU is missing: no fallback
     stream = torch.cuda.ExternalStream(ctx.stream)     # the library's compute stream, so events see its kernels
 
-    blocks_per_gpu = int(args.slot_gib * (1 << 30)) // BLOCK
-    n_bytes = blocks_per_gpu * BLOCK
-    n_total_blocks = blocks_per_gpu * world
-    top_level, ranges = sharded.fixed_ranges(blocks_per_gpu, world)
-    first_block = ranges[rank][0]
+    if args.total_gib > 0:                             # strong scaling: one slot, 2^T-aligned chunks dealt evenly
+        n_total_blocks = int(args.total_gib * (1 << 30)) // BLOCK
+        top_level, ranges = sharded.plan_block_ranges(n_total_blocks, world)
+        scaling = "strong"
+    else:                                              # weak scaling: every rank holds --slot-gib of one N x larger slot
+        blocks_per_gpu = int(args.slot_gib * (1 << 30)) // BLOCK
+        n_total_blocks = blocks_per_gpu * world
+        top_level, ranges = sharded.fixed_ranges(blocks_per_gpu, world)
+        scaling = "weak"
+    first_block, my_blocks = ranges[rank]
+    n_bytes = my_blocks * BLOCK
 
     d_slot = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
     ctx.fill_synthetic_dev(SEED, first_block * (BLOCK // 8), n_bytes, d_slot.data_ptr())
@@ -270,7 +279,7 @@ def main() -> None:
     ev_s, wall_s, root = timed(commit_resident, args.steps)
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    total_bytes = n_bytes * world
+    total_bytes = n_total_blocks * BLOCK
     value = total_bytes * args.steps / ev_s / 1e9
     perms_step = total_perms(n_total_blocks)
 
@@ -317,6 +326,20 @@ def main() -> None:
         except Exception:
             pass
 
+    # ---- BASELINE config 2: 2^20 independent permutations (kernel time, best of 10) ----
+    n_perm = 1 << 20
+    d_pin = torch.empty(96 * n_perm, dtype=torch.uint8, device="cuda")
+    d_pout = torch.empty_like(d_pin)
+    ctx.fill_synthetic_dev(1, 0, 96 * n_perm, d_pin.data_ptr())
+    ctx.permutation_batch_dev(d_pin.data_ptr(), d_pout.data_ptr(), n_perm)
+    best_perm = None
+    for _ in range(10):
+        p_ev, _, _ = timed(lambda: ctx.permutation_batch_dev(d_pin.data_ptr(), d_pout.data_ptr(), n_perm), 1)
+        best_perm = p_ev if best_perm is None or p_ev < best_perm else best_perm
+    perm_batch = {"n": n_perm, "ms": 1e3 * best_perm, "perms_per_s": n_perm / best_perm,
+                  "note": "k_permutation_batch incl. to/from Montgomery form (6 extra modmuls per permutation), per GPU"}
+    del d_pin, d_pout
+
     # ---- end to end through the host-buffer ABI ----
     e2e = None
     if not args.no_e2e:
@@ -341,7 +364,7 @@ def main() -> None:
             r2 = commit_host()
         _, e2e_wall, r2 = timed(commit_host, args.steps)
         assert r2 == root, "host-buffer path and resident path disagree on the slot root"
-        e2e = {"value": total_bytes * args.steps / e2e_wall / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n_bytes * world, "d2h_bytes_per_step": 32 * world,
+        e2e = {"value": total_bytes * args.steps / e2e_wall / 1e9, "unit": "GB/s", "h2d_bytes_per_step": total_bytes, "d2h_bytes_per_step": 32 * world,
                "ms_per_step": 1e3 * e2e_wall / args.steps,
                "api": "cdx_slot_commit_host" if world == 1 else "cdx_slot_commit_range_host + NCCL all-gather + cdx_slot_set_top_dev",
                "timing": "wall clock bracketed by barrier + cudaDeviceSynchronize, max over ranks"}
@@ -364,16 +387,18 @@ def main() -> None:
     if rank == 0:
         line = {
             "metric": "slot commit GB/s (with Poseidon2 perms/s)", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "u32x8 (BN254 Fr, 256-bit Montgomery integers)", "data": "synthetic",
-            "config": {"workload": f"single {args.slot_gib:g} GiB-per-GPU synthetic slot ({n_total_blocks} blocks of 64 KiB, 2048-byte cells): "
-                                   "cell sponge + block trees + slot tree + root",
+            "config": {"workload": (f"single {args.total_gib:g} GiB synthetic slot split over {world} GPU(s)" if args.total_gib > 0 else
+                                    f"single {args.slot_gib:g} GiB-per-GPU synthetic slot") +
+                                   f" ({n_total_blocks} blocks of 64 KiB, 2048-byte cells): cell sponge + block trees + slot tree + root",
                        "bytes_per_step": total_bytes, "cell_size": CELL, "block_size": BLOCK, "seed": SEED,
                        "parallelism": "1 GPU" if world == 1 else f"{world} ranks x block-range shards, all-gather of level-{top_level} roots",
-                       "l2": "inputs (10 GiB per GPU) are larger than L2; no flush needed"},
+                       "l2": f"inputs ({n_bytes / 2**30:.1f} GiB per GPU) are larger than L2; no flush needed"},
             "perms_per_s": perms_step * args.steps / ev_s, "perms_per_step": perms_step,
             "slot_root": hex(root), "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "perm_batch_2^20": perm_batch,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -123,3 +123,30 @@ def test_permutation_batch_2_17_vs_oracle(ctx, orc, torch_mod):
     torch.cuda.synchronize()
     inp = a.cpu().numpy().tobytes()
     assert b.cpu().numpy().tobytes() == orc.permutation_batch_bytes(inp)     # inputs are arbitrary 256-bit values: taken mod r
+
+
+def test_dataset_commit_small_vs_oracle(ctx, orc, torch_mod):
+    """BASELINE config 5 in miniature: 13 slots of mixed size (odd nodes in the dataset tree), slot 3 sampled"""
+    dataset = importlib.import_module(PKG + ".dataset")
+    blocks = dataset.draw_slot_blocks(13, 3 * 65536, 40 * 65536, seed=99, pow2_slot=3, pow2_blocks=16)
+    assert blocks[3] == 16 and len(set(blocks)) > 5
+    res = dataset.commit_dataset(ctx, blocks, 99, 3, 1234567, 20, max_depth=32, max_log2_nslots=8)
+    # every slot root against the oracle over the same synthetic bytes (bench.py's numpy twin of the device generator)
+    import bench
+    for k in (0, 3, 7, 12):
+        data = bench.synthetic_bytes_host(dataset.slot_seed(99, k), 0, blocks[k] * 65536)
+        root, _, _ = orc.commit_slot((data.ctypes.data, blocks[k] * 65536), n_threads=4)
+        assert res.slot_roots[k] == root
+    layers = orc.merkle_layers(res.slot_roots)
+    assert res.dataset_layers == layers and res.dataset_root == layers[-1][0]
+    assert orc.reconstruct_root(res.slot_roots[3], 3, 13, res.slot_proof[:len(layers) - 1]) == res.dataset_root
+    assert res.slot_proof[len(layers) - 1:] == [0] * (8 - (len(layers) - 1))
+    n_cells = 16 * 32
+    assert res.cell_indices == [orc.cell_index(1234567, res.slot_roots[3], n_cells, c) for c in range(1, 21)]
+    for ci, path, leaf in zip(res.cell_indices, res.merkle_paths, res.cell_hashes):
+        blk = orc.reconstruct_root(leaf, ci % 32, 32, path[:5])
+        assert orc.reconstruct_root(blk, ci // 32, 16, path[5:9]) == res.slot_roots[3]
+    bins = dataset.lpt_assign(blocks, 4)
+    assert sorted(k for b in bins for k in b) == list(range(13))
+    loads = [sum(blocks[k] for k in b) for b in bins]
+    assert max(loads) <= 1.34 * sum(blocks) / 4
