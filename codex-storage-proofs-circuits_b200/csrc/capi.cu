@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -29,6 +30,7 @@ struct cdx_ctx {
   void* d_stage[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;
   uint64_t launches = 0;
+  bool plain_loads = false;            // CODEX_COMMIT_PLAIN_LOADS=1: per-thread global loads instead of the TMA-staged rows (A/B only)
   char err[256] = {0};
 };
 
@@ -102,6 +104,7 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   cdx_ctx* ctx = new (std::nothrow) cdx_ctx();
   if (!ctx) return CDX_ERR_ALLOC;
   ctx->device = device;
+  if (const char* v = getenv("CODEX_COMMIT_PLAIN_LOADS")) ctx->plain_loads = v[0] == '1';
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) {   // keep freed tree buffers in the pool instead of returning them to the driver
@@ -164,6 +167,48 @@ struct DevBuf {
   uint8_t* u8() const { return static_cast<uint8_t*>(p); }
 };
 
+// The cell sponge, with TMA-staged rows whenever the cell geometry allows 32-byte tensor boxes (cell size a multiple of
+// 32, 16-byte aligned base, < 2^32 cells); otherwise the same sponge over per-thread global loads.  The tensor map
+// is encoded on the host per launch (cuTensorMapEncodeTiled, resolved through the runtime so libcuda is not a link
+// dependency) and travels as a __grid_constant__ kernel parameter.
+typedef int (*encode_tiled_fn)(void* tensorMap, int dataType, unsigned rank, void* globalAddress, const unsigned long long* globalDim,
+                               const unsigned long long* globalStrides, const unsigned* boxDim, const unsigned* elementStrides, int interleave,
+                               int swizzle, int l2Promotion, int oobFill);
+
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+
+static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, size_t cell_size, uint8_t* d_out, cudaStream_t st) {
+  encode_tiled_fn encode = ctx->plain_loads ? nullptr : get_encode_tiled();
+  if (encode && cell_size % CDX_SEG_BYTES == 0 && cell_size >= 64 && cell_size < (1u << 31) && (uintptr_t)d_data % 16 == 0 && n_cells < (1ull << 32)) {
+    TensorMap2D tmap;
+    const unsigned long long dims[2] = {(unsigned long long)cell_size, (unsigned long long)n_cells};   // innermost first
+    const unsigned long long strides[1] = {(unsigned long long)cell_size};                             // bytes between rows
+    const unsigned box[2] = {CDX_SEG_BYTES, 32u};
+    const unsigned estr[2] = {1u, 1u};
+    // CU_TENSOR_MAP_DATA_TYPE_UINT8 = 0, INTERLEAVE_NONE = 0, SWIZZLE_NONE = 0, L2_PROMOTION_NONE = 0, FLOAT_OOB_FILL_NONE = 0 (zeros)
+    const int rc = encode(&tmap, 0, 2, const_cast<void*>(d_data), dims, strides, box, estr, 0, 0, 0, 0);
+    if (rc != 0) return fail(ctx, CDX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", rc);
+    const size_t smem = 128 + (CDX_BLOCK / 32) * (CDX_RING_SLOTS * CDX_BOX_BYTES + 8 * CDX_RING_SLOTS);
+    k_hash_cells_tma<<<grid_for(n_cells), CDX_BLOCK, smem, st>>>(tmap, n_cells, (uint32_t)cell_size, d_out);
+  } else {
+    k_hash_cells<<<grid_for(n_cells), CDX_BLOCK, 0, st>>>((const uint32_t*)d_data, n_cells, (uint32_t)(cell_size / 4), d_out);
+  }
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return CDX_OK;
+}
+
 // ---- hash layer ---------------------------------------------------------------------------------------------
 
 extern "C" int cdx_permutation_batch_dev(cdx_ctx* ctx, const void* d_in, void* d_out, size_t n, void* stream) {
@@ -214,10 +259,12 @@ extern "C" int cdx_hash_bytes_batch_host(cdx_ctx* ctx, const uint8_t* data, size
   CU_TRY(ctx, di.alloc(len * n_items, ctx->stream));
   CU_TRY(ctx, dout.alloc(32 * n_items, ctx->stream));
   if (len) CU_TRY(ctx, cudaMemcpyAsync(di.p, data, len * n_items, cudaMemcpyHostToDevice, ctx->stream));
-  if (len % 4 == 0 && len > 0)   // cudaMalloc'd base is 256-byte aligned, so every item is word aligned
-    LAUNCH(ctx, k_hash_cells, n_items, ctx->stream, (const uint32_t*)di.p, n_items, (uint32_t)(len / 4), dout.u8());
-  else
+  if (len % 4 == 0 && len > 0) {   // pool allocations are 256-byte aligned, so every item is word aligned
+    int rc = launch_hash_cells(ctx, di.p, n_items, len, dout.u8(), ctx->stream);
+    if (rc) return rc;
+  } else {
     LAUNCH(ctx, k_hash_bytes_any, n_items, ctx->stream, di.u8(), n_items, (uint32_t)len, dout.u8());
+  }
   CU_TRY(ctx, cudaMemcpyAsync(out, dout.p, 32 * n_items, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return CDX_OK;
@@ -229,8 +276,7 @@ extern "C" int cdx_hash_cells_dev(cdx_ctx* ctx, const void* d_data, size_t n_cel
   if ((uintptr_t)d_data % 16 || (uintptr_t)d_out % 16) return fail(ctx, CDX_ERR_ARG, "buffers must be 16-byte aligned");
   if (n_cells == 0) return CDX_OK;
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  LAUNCH(ctx, k_hash_cells, n_cells, st, (const uint32_t*)d_data, n_cells, (uint32_t)(cell_size / 4), (uint8_t*)d_out);
-  return CDX_OK;
+  return launch_hash_cells(ctx, d_data, n_cells, cell_size, (uint8_t*)d_out, st);
 }
 
 extern "C" int cdx_compress_batch_host(cdx_ctx* ctx, const uint8_t* x, const uint8_t* y, const uint32_t* keys, size_t n, uint8_t* out) {
@@ -487,7 +533,8 @@ extern "C" int cdx_slot_commit_range_dev(cdx_ctx* ctx, const void* d_data, size_
   rc = slot_alloc(ctx, n_local_bytes / block_size, cell_size, block_size, first_block, n_total_blocks, top_level, st, &s);
   if (rc) return rc;
   auto body = [&]() -> int {
-    LAUNCH(ctx, k_hash_cells, s->n_local_cells, st, (const uint32_t*)d_data, (size_t)s->n_local_cells, (uint32_t)(cell_size / 4), s->forest[0]);
+    int r = launch_hash_cells(ctx, d_data, (size_t)s->n_local_cells, cell_size, s->forest[0], st);
+    if (r) return r;
     return build_local_trees(s);
   };
   rc = body();
@@ -567,8 +614,8 @@ static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
       CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, ctx->copy_stream));
       CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
       CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
-      LAUNCH(ctx, k_hash_cells, nb * cpb, cs, (const uint32_t*)ctx->d_stage[b], nb * cpb, (uint32_t)(cell_size / 4),
-             s->forest[0] + 32 * done * cpb);
+      int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, s->forest[0] + 32 * done * cpb, cs);
+      if (hr) return hr;
       CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], cs));
       done += nb;
     }

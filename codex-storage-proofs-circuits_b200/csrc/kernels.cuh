@@ -58,6 +58,110 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_hash_cells(const uint32_t* __rest
   st_felt(out + 32 * i, from_mont(sponge2_bytes(ld, cell_words * 4u)));
 }
 
+// K2 with TMA-staged rows.  Same arithmetic; the slot bytes reach the threads through shared memory instead of
+// per-thread global loads.  The slot is described to the TMA unit as a 2-D byte tensor [n_cells][cell_bytes]; a warp
+// (32 consecutive cells) fetches the next 32-byte column segment of all its cells with ONE tensor copy
+// (cp.async.bulk.tensor.2d -> SASS UTMALDG) issued by one elected lane into a ring of CDX_RING_SLOTS boxes of
+// 32 rows x 32 B, two segments ahead of the sponge.  One mbarrier per (warp, ring slot): expect_tx = 1024 B, the phase
+// completes when the box has landed (rows past the end of the slot are zero-filled by the TMA unit and still counted).
+// Lane l only ever reads row l, and a box is overwritten only after the step that last read it, so there is no
+// cross-thread hand-shake beyond the warp being convergent.
+//   HBM traffic: each 32-byte sector of the slot is fetched exactly once.
+#define CDX_RING_SLOTS 6
+#define CDX_SEG_BYTES 32u
+#define CDX_BOX_BYTES (32u * CDX_SEG_BYTES)
+
+struct RowRing {
+  // Deliberately (almost) stateless: everything is re-derived from the step number and the thread indices once per
+  // step (a step is one permutation, ~45 k instructions), so nothing of the pipeline lives in registers across the
+  // permutation -- the hot loops then get the same register allocation as in the plain-load kernel.
+  const void* tmap;       // the slot as a 2-D tensor (kernel parameter space: no register cost)
+  uint32_t smem_base;     // 128-byte aligned shared-space base of the CTA's rings
+  uint32_t cell_bytes;
+
+  __device__ __forceinline__ uint32_t warp() const { return threadIdx.x >> 5; }
+  __device__ __forceinline__ uint32_t boxes() const { return smem_base + warp() * (CDX_RING_SLOTS * CDX_BOX_BYTES); }
+  __device__ __forceinline__ uint32_t bars() const {
+    return smem_base + (blockDim.x >> 5) * (CDX_RING_SLOTS * CDX_BOX_BYTES) + warp() * (8u * CDX_RING_SLOTS);
+  }
+  __device__ __forceinline__ int last_seg() const { return (int)(cell_bytes / CDX_SEG_BYTES) - 1; }
+  // segments wanted resident-or-in-flight / needed landed when step j starts (-1 before the first step)
+  __device__ __forceinline__ int want_at(int j) const {
+    if (j < 0) return -1;
+    const int w = (int)((62u * (uint32_t)j) / CDX_SEG_BYTES) + (CDX_RING_SLOTS - 1);
+    return w < last_seg() ? w : last_seg();
+  }
+  __device__ __forceinline__ int need_at(int j) const {
+    if (j < 0) return -1;
+    const int h = (int)((62u * (uint32_t)j + 67u) / CDX_SEG_BYTES);
+    return h < last_seg() ? h : last_seg();
+  }
+  // step j of the sponge reads padded-stream bytes [62 j, 62 j + 68): make those segments resident, keep two ahead
+  __device__ __forceinline__ void begin_step(uint32_t j) const {
+    const int issued = want_at((int)j - 1), want = want_at((int)j);
+    if ((threadIdx.x & 31u) == 0) {
+      const uint32_t row0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);          // first cell (tensor row) of this warp
+      for (int g = issued + 1; g <= want; ++g) {
+        const uint32_t slot = (uint32_t)g % CDX_RING_SLOTS;
+        const uint32_t bar = bars() + 8u * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CDX_BOX_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                         boxes() + slot * CDX_BOX_BYTES),
+                     "l"(tmap), "r"((uint32_t)g * CDX_SEG_BYTES), "r"(row0), "r"(bar)
+                     : "memory");
+      }
+    }
+    __syncwarp();
+    for (int g = need_at((int)j - 1) + 1; g <= need_at((int)j); ++g) {
+      const uint32_t bar = bars() + 8u * ((uint32_t)g % CDX_RING_SLOTS);
+      const uint32_t parity = ((uint32_t)g / CDX_RING_SLOTS) & 1u;
+      uint32_t done;
+      do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+      } while (!done);
+    }
+  }
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+    if (i >= (cell_bytes >> 2)) return i == (cell_bytes >> 2) ? 1u : 0u;
+    const uint32_t seg = i >> 3, slot = seg % CDX_RING_SLOTS;
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(boxes() + slot * CDX_BOX_BYTES + (threadIdx.x & 31u) * CDX_SEG_BYTES + 4u * (i & 7u)) : "memory");
+    return v;
+  }
+};
+
+struct alignas(64) TensorMap2D {   // layout-compatible with CUtensorMap (128 opaque bytes, 64-byte aligned)
+  unsigned long long opaque[16];
+};
+
+// cell_bytes % 32 == 0; dynamic shared memory: 128 B slack + warps x (CDX_RING_SLOTS x 1 KiB) + barriers
+__global__ void __launch_bounds__(CDX_BLOCK) k_hash_cells_tma(const __grid_constant__ TensorMap2D tmap, size_t n_cells, uint32_t cell_bytes,
+                                                              uint8_t* __restrict__ out) {
+  extern __shared__ uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t warp_first = i - lane;
+  if (warp_first >= n_cells) return;                                   // whole warp past the end (warp-uniform)
+  const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem) + 127u) & ~127u;   // tensor copies need 128-byte aligned boxes
+  const uint32_t bars = smem_base + n_warps * (CDX_RING_SLOTS * CDX_BOX_BYTES) + warp * (8u * CDX_RING_SLOTS);
+  if (lane == 0) {
+#pragma unroll
+    for (uint32_t s = 0; s < CDX_RING_SLOTS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  RowRing ld;
+  ld.tmap = &tmap;
+  ld.smem_base = smem_base;
+  ld.cell_bytes = cell_bytes;
+  const Fr h = from_mont(sponge2_bytes(ld, cell_bytes));               // lanes past the end hash zero-filled rows, store nothing
+  if (i < n_cells) st_felt(out + 32 * i, h);
+}
+
 // byte strings of arbitrary length/alignment (test-vector suite: n = 0..80).   testvectors.nim:41-46
 __global__ void __launch_bounds__(CDX_BLOCK) k_hash_bytes_any(const uint8_t* __restrict__ data, size_t n_items, uint32_t len,
                                                               uint8_t* __restrict__ out) {

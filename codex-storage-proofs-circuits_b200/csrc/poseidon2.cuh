@@ -98,7 +98,7 @@ CDX_D Fr compress_keyed(const Fr& x, const Fr& y, uint32_t key) {
 // memory, registers).  Chunk k covers stream bytes [31k, 31k+31) and is returned as a standard-form integer
 // < 2^248 (Slot.hs:243-270, README.md:86-99).
 template <class LoadWord>
-CDX_D Fr read_chunk(LoadWord ld, uint32_t k) {
+CDX_D Fr read_chunk(const LoadWord& ld, uint32_t k) {
   const uint32_t byte_off = 31u * k;
   const uint32_t w0 = byte_off >> 2;
   const uint32_t sh = (byte_off & 3u) * 8u;
@@ -123,6 +123,7 @@ struct AlignedWords {
   const uint32_t* words;
   uint32_t n_words;
   CDX_D uint32_t operator()(uint32_t i) const { return i < n_words ? words[i] : (i == n_words ? 1u : 0u); }
+  CDX_D void begin_step(uint32_t) const {}   // loaders that stage data (RowRing in kernels.cuh) advance their pipeline here
 };
 
 // padded-stream loader for an arbitrary byte string (any alignment, any length)
@@ -134,6 +135,7 @@ struct AnyBytes {
     const uint32_t j = 4u * i;
     return byte_at(j) | (byte_at(j + 1) << 8) | (byte_at(j + 2) << 16) | (byte_at(j + 3) << 24);
   }
+  CDX_D void begin_step(uint32_t) const {}
 };
 
 // number of field elements of a len-byte string: floor(len/31) + 1   (Slot.hs:243-250)
@@ -143,7 +145,7 @@ CDX_HD uint32_t n_chunks(uint32_t len) { return len / 31u + 1u; }
 // One loop, one inlined permutation: step j absorbs elements (2j, 2j+1) of  chunks ++ pad,
 // pad = [1] if the chunk count is odd, [1,0] if even.              Sponge.hs:30-43, blocks/bn254.nim:23-29
 template <class LoadWord>
-CDX_D Fr sponge2_bytes(LoadWord ld, uint32_t len_bytes) {
+CDX_D Fr sponge2_bytes(const LoadWord& ld, uint32_t len_bytes) {
   const uint32_t n = n_chunks(len_bytes);
   const uint32_t n_perm = n / 2u + 1u;
   const Fr one = {CDX_ONE_INIT};
@@ -151,6 +153,7 @@ CDX_D Fr sponge2_bytes(LoadWord ld, uint32_t len_bytes) {
 #pragma unroll 1
   for (uint32_t j = 0; j < n_perm; ++j) {
     const uint32_t k = 2u * j;
+    ld.begin_step(j);                 // step j reads padded-stream bytes [62 j, 62 j + 68)
     if (k < n) s0 = add_mod(s0, to_mont(read_chunk(ld, k)));
     else s0 = add_mod(s0, one);
     if (k + 1 < n) s1 = add_mod(s1, to_mont(read_chunk(ld, k + 1)));

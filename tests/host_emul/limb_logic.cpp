@@ -23,11 +23,13 @@ void emul_permutation(const uint8_t* in, uint8_t* out) {
   store(out, from_mont(x)); store(out + 32, from_mont(y)); store(out + 64, from_mont(z));
 }
 void emul_hash_bytes(const uint8_t* data, uint32_t len, uint8_t* out) {
-  store(out, from_mont(sponge2_bytes(AnyBytes{data, len}, len)));
+  AnyBytes ld{data, len};
+  store(out, from_mont(sponge2_bytes(ld, len)));
 }
 // aligned-cell path: data must be 4-byte aligned and len % 4 == 0
 void emul_hash_cell_aligned(const uint8_t* data, uint32_t len, uint8_t* out) {
-  store(out, from_mont(sponge2_bytes(AlignedWords{(const uint32_t*)data, len / 4}, len)));
+  AlignedWords ld{(const uint32_t*)data, len / 4};
+  store(out, from_mont(sponge2_bytes(ld, len)));
 }
 void emul_sponge(const uint8_t* elems, uint32_t n, int rate, uint8_t* out) {
   auto get = [&](uint32_t i) { return load(elems + 32 * i); };
