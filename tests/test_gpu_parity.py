@@ -152,9 +152,12 @@ def test_slot_roots_ragged_block_counts(ctx, orc, n_blocks):
         assert slot.root == root
 
 
-@pytest.mark.parametrize("cell_size,block_size,n_cells", [(128, 4096, 256), (256, 4096, 64), (2048, 2048, 8), (64, 128, 10), (4096, 65536, 48)])
+@pytest.mark.parametrize("cell_size,block_size,n_cells", [(128, 4096, 256), (256, 4096, 64), (2048, 2048, 8), (64, 128, 10), (4096, 65536, 48),
+                                                          (96, 192, 10), (32, 64, 6), (2048, 65536, 32 * 35), (160, 320, 70)])
 def test_other_cell_and_block_sizes(ctx, orc, cell_size, block_size, n_cells):
-    """testMain.hs small config (128/4096), one-cell blocks, two-cell blocks, bigger cells"""
+    """testMain.hs small config (128/4096), one-cell blocks, two-cell blocks, bigger cells; TMA-staged rows with a
+    partial last warp (rows past the end are zero-filled by the TMA unit), and geometries that take the plain-load
+    kernel (cell size below 64 bytes)"""
     seed = 999
     with ctx.slot_commit_fake(seed, n_cells, cell_size, block_size) as slot:
         root, bh, ch = orc.commit_fake_slot(seed, n_cells, cell_size, block_size, want_cells=True)
