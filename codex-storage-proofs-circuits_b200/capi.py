@@ -51,6 +51,7 @@ SYMBOLS = {
     "cdx_slot_shape": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32), C.POINTER(_u32)]),
     "cdx_slot_read_layer": (_int, [_vp, _int, _u32, _u64, _u64, _vp]),
     "cdx_slot_cell_paths": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "cdx_reconstruct_roots_host": (_int, [_vp, _vp, _vp, _u64, _vp, _sz, _sz, _sz, _vp]),
     "cdx_cell_indices": (_int, [_vp, _vp, _vp, _u64, _sz, _vp]),
     "cdx_fake_cells_host": (_int, [_vp, _u64, _u64, _sz, _sz, _vp]),
     "cdx_fake_cells_dev": (_int, [_vp, _u64, _u64, _sz, _sz, _vp, _vp]),
@@ -253,6 +254,19 @@ class Context:
 
     def hash_cells_dev(self, d_data: int, n_cells: int, cell_size: int, d_out: int, stream: int = 0):
         self._chk(self.lib.cdx_hash_cells_dev(self.h, d_data, n_cells, cell_size, d_out, stream))
+
+    def reconstruct_roots(self, leaves: Sequence[int], indices: Sequence[int], n_leaves: int, paths: Sequence[Sequence[int]],
+                          depth: Optional[int] = None) -> List[int]:
+        """batched reconstructRoot (merkle.nim:51-74): one root per (leaf, index, path)"""
+        n = len(leaves)
+        stride = len(paths[0]) if n else 0
+        depth = stride if depth is None else depth
+        bl, bp = pack(leaves), b"".join(pack(p) for p in paths)
+        idx = (C.c_uint64 * max(n, 1))(*indices)
+        out = C.create_string_buffer(32 * n if n else 1)
+        self._chk(self.lib.cdx_reconstruct_roots_host(self.h, _addr(bl) if n else None, C.addressof(idx), n_leaves,
+                                                      _addr(bp) if bp else None, stride, depth, n, C.addressof(out)))
+        return unpack(out.raw[:32 * n])
 
     # ---- sampling / data ----
     def cell_indices(self, entropy: int, slot_root: int, n_cells: int, n_samples: int) -> List[int]:

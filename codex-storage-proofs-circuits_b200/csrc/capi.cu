@@ -806,6 +806,28 @@ extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indic
   return CDX_OK;
 }
 
+extern "C" int cdx_reconstruct_roots_host(cdx_ctx* ctx, const uint8_t* leaves, const uint64_t* indices, uint64_t n_leaves, const uint8_t* paths,
+                                          size_t path_stride, size_t depth, size_t n, uint8_t* roots_out) {
+  if (!ctx || !leaves || !indices || !roots_out || (!paths && depth)) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  if (depth > path_stride || depth > 64) return fail(ctx, CDX_ERR_RANGE, "depth %zu exceeds the path stride %zu", depth, path_stride);
+  for (size_t i = 0; i < n; ++i)
+    if (indices[i] >= n_leaves) return fail(ctx, CDX_ERR_RANGE, "leaf index %llu >= %llu", (unsigned long long)indices[i], (unsigned long long)n_leaves);
+  if (n == 0) return CDX_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf dl, di, dp, dout;
+  CU_TRY(ctx, dl.alloc(32 * n, ctx->stream));
+  CU_TRY(ctx, di.alloc(8 * n, ctx->stream));
+  CU_TRY(ctx, dp.alloc(32 * n * path_stride, ctx->stream));
+  CU_TRY(ctx, dout.alloc(32 * n, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(dl.p, leaves, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(di.p, indices, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (path_stride) CU_TRY(ctx, cudaMemcpyAsync(dp.p, paths, 32 * n * path_stride, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, k_reconstruct_roots, n, ctx->stream, dl.u8(), (const uint64_t*)di.p, n_leaves, dp.u8(), (uint32_t)path_stride, (uint32_t)depth, n, dout.u8());
+  CU_TRY(ctx, cudaMemcpyAsync(roots_out, dout.p, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return CDX_OK;
+}
+
 // ---- sampling and data source -------------------------------------------------------------------------------
 
 extern "C" int cdx_cell_indices(cdx_ctx* ctx, const uint8_t entropy[32], const uint8_t slot_root[32], uint64_t n_cells, size_t n_samples, uint64_t* indices) {

@@ -254,6 +254,29 @@ __global__ void k_gather_paths(PathPlan plan, const uint64_t* __restrict__ cells
   reinterpret_cast<uint4*>(out + 32 * ((size_t)s * max_depth + lvl))[half] = v;
 }
 
+// Verifier walk, one proof per thread: reconstructRoot (merkle.nim:51-74) == RootFromMerklePath (merkle.circom:44-114).
+// paths: n x stride elements (only the first `depth` of each are walked), leaves/indices: n.
+__global__ void __launch_bounds__(CDX_BLOCK) k_reconstruct_roots(const uint8_t* __restrict__ leaves, const uint64_t* __restrict__ indices,
+                                                                 uint64_t n_leaves, const uint8_t* __restrict__ paths, uint32_t stride,
+                                                                 uint32_t depth, size_t n, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t j = indices[i], m = n_leaves;
+  Fr h = to_mont(ld_felt(leaves + 32 * i));
+  uint32_t bottom = 1;
+#pragma unroll 1
+  for (uint32_t l = 0; l < depth; ++l) {
+    const Fr p = to_mont(ld_felt(paths + 32 * ((size_t)i * stride + l)));
+    if (j & 1) h = compress_keyed(p, h, bottom);              // odd index: the sibling is on the left
+    else if (j == m - 1) h = compress_keyed(h, p, bottom + 2);   // last and even: a single child (odd node)
+    else h = compress_keyed(h, p, bottom);
+    bottom = 0;
+    j >>= 1;
+    m = (m + 1) >> 1;
+  }
+  st_felt(out + 32 * i, from_mont(h));
+}
+
 // K5: sampled cell indices.                                       sample/bn254.nim:16-27, types/bn254.nim:47-59
 __global__ void k_cell_indices(const uint8_t* __restrict__ entropy_root /* 64 B */, uint64_t mask, uint32_t n_samples,
                                uint64_t* __restrict__ out) {

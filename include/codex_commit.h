@@ -152,6 +152,13 @@ int cdx_slot_read_layer(const cdx_slot* slot, int tree, uint32_t level, uint64_t
  * For a sharded slot only levels held by this rank are filled, the rest are left zero (sum over ranks = path). */
 int cdx_slot_cell_paths(const cdx_slot* slot, const uint64_t* cell_indices, size_t n_samples, size_t max_depth, uint8_t* out, uint8_t* leaf_out);
 
+/* Batched verifier walk: roots_out[i] = the root reconstructed from leaf i at index indices[i] in a tree of n_leaves
+ * leaves along the first `depth` elements of its path (paths are n x path_stride elements, so padded paths can be
+ * passed as they are).  Replaces: reconstructRoot / checkMerkleProof -- nim/merkle.nim:51-77 (also the check inside
+ * mergeMerkleProofs, :88-89); same semantics as RootFromMerklePath, circuit/codex/merkle.circom:44-114. */
+int cdx_reconstruct_roots_host(cdx_ctx* ctx, const uint8_t* leaves, const uint64_t* indices, uint64_t n_leaves, const uint8_t* paths,
+                               size_t path_stride, size_t depth, size_t n, uint8_t* roots_out);
+
 /* ---- sampling and data source --------------------------------------------------------------------------- */
 
 /* indices[c-1] = low log2(n_cells) bits of sponge2([entropy, slot_root, c]), c = 1..n_samples.

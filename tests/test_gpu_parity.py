@@ -226,6 +226,27 @@ def test_every_cell_path_of_a_ragged_slot(ctx, orc, pyorc):
         assert orc.reconstruct_root(blk, i // 32, 5, paths[i][5:8]) == root
 
 
+def test_batched_root_reconstruction(ctx, orc, pyorc):
+    """cdx_reconstruct_roots_host == reconstructRoot (merkle.nim:51-74) for every leaf of trees with 1..20 leaves, and the
+    two-stage check of padded cell paths (Slot.hs:189-217)"""
+    for n in (1, 2, 3, 5, 8, 13, 20):
+        layers = orc.merkle_layers([1000 + i for i in range(1, n + 1)])
+        proofs = [pyorc.merkle_proof(layers, j) for j in range(n)]
+        got = ctx.reconstruct_roots([p.leaf_value for p in proofs], list(range(n)), n, [p.merkle_path for p in proofs])
+        assert got == [layers[-1][0]] * n
+    seed, n_cells = 4242, 5 * 32
+    with ctx.slot_commit_fake(seed, n_cells) as slot:
+        idx = [0, 31, 32, 77, 159]
+        paths, leaves = slot.cell_paths(idx, 32)
+        block_roots = ctx.reconstruct_roots(leaves, [i % 32 for i in idx], 32, paths, depth=5)
+        assert block_roots == [slot.read_layer(1, 0, i // 32, 1)[0] for i in idx]
+        slot_roots = ctx.reconstruct_roots(block_roots, [i // 32 for i in idx], 5, [p[5:] for p in paths], depth=3)
+        assert slot_roots == [slot.root] * len(idx)
+        bad = [list(p) for p in paths]
+        bad[2][1] ^= 1
+        assert ctx.reconstruct_roots(leaves, [i % 32 for i in idx], 32, bad, depth=5)[2] != block_roots[2]
+
+
 def test_paths_errors(ctx, pkg):
     with ctx.slot_commit_fake(1, 64) as slot:
         with pytest.raises(pkg.CodexCommitError) as e:
