@@ -39,6 +39,7 @@ SYMBOLS = {
     "cdx_merkle_root_host": (_int, [_vp, _vp, _sz, _vp]),
     "cdx_slot_commit_host": (_int, [_vp, _vp, _sz, _sz, _sz, _pp]),
     "cdx_slot_commit_dev": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _pp]),
+    "cdx_slot_commit_file": (_int, [_vp, C.c_char_p, _u64, _sz, _sz, _sz, _pp]),
     "cdx_slot_commit_fake": (_int, [_vp, _u64, _sz, _sz, _sz, _pp]),
     "cdx_slot_commit_range_dev": (_int, [_vp, _vp, _sz, _sz, _sz, _u64, _u64, _int, _vp, _pp]),
     "cdx_slot_commit_range_host": (_int, [_vp, _vp, _sz, _sz, _sz, _u64, _u64, _int, _pp]),
@@ -46,6 +47,9 @@ SYMBOLS = {
     "cdx_slot_subtree_root_count": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "cdx_slot_subtree_roots_dev": (_vp, [_vp]),
     "cdx_slot_set_top_dev": (_int, [_vp, _vp, _u64, _vp]),
+    "cdx_slot_export_size": (_sz, [_vp]),
+    "cdx_slot_export": (_int, [_vp, _vp, _sz]),
+    "cdx_slot_import": (_int, [_vp, _vp, _sz, _pp]),
     "cdx_slot_free": (None, [_vp]),
     "cdx_slot_root": (_int, [_vp, _vp]),
     "cdx_slot_shape": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32), C.POINTER(_u32)]),
@@ -232,6 +236,16 @@ class Context:
         self._chk(self.lib.cdx_slot_commit_dev(self.h, d_data, n_bytes, cell_size, block_size, stream, C.byref(h)))
         return Slot(self, h)
 
+    def slot_commit_file(self, path: str, n_bytes: int, offset: int = 0, cell_size: int = 2048, block_size: int = 65536) -> "Slot":
+        h = C.c_void_p()
+        self._chk(self.lib.cdx_slot_commit_file(self.h, os.fsencode(path), offset, n_bytes, cell_size, block_size, C.byref(h)))
+        return Slot(self, h)
+
+    def slot_import(self, image: bytes) -> "Slot":
+        h = C.c_void_p()
+        self._chk(self.lib.cdx_slot_import(self.h, _addr(image), len(image), C.byref(h)))
+        return Slot(self, h)
+
     def slot_commit_fake(self, seed: int, n_cells: int, cell_size: int = 2048, block_size: int = 65536) -> "Slot":
         h = C.c_void_p()
         self._chk(self.lib.cdx_slot_commit_fake(self.h, seed & (2**64 - 1), n_cells, cell_size, block_size, C.byref(h)))
@@ -341,6 +355,14 @@ class Slot:
         self.ctx._chk(self.ctx.lib.cdx_slot_cell_paths(self.h, C.addressof(idx), n, max_depth, C.addressof(out), C.addressof(leaf)))
         flat = unpack(out.raw[:32 * n * max_depth])
         return [flat[i * max_depth:(i + 1) * max_depth] for i in range(n)], unpack(leaf.raw[:32 * n])
+
+    def export(self) -> bytes:
+        n = self.ctx.lib.cdx_slot_export_size(self.h)
+        if n == 0:
+            raise CodexCommitError(CDX_ERR_STATE, "only whole slots with their top tree can be exported")
+        buf = C.create_string_buffer(n)
+        self.ctx._chk(self.ctx.lib.cdx_slot_export(self.h, C.addressof(buf), n))
+        return buf.raw
 
     def subtree_roots(self):
         first, cnt = C.c_uint64(), C.c_uint64()

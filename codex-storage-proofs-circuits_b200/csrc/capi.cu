@@ -5,11 +5,15 @@
 
 #include <cuda_runtime.h>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -29,6 +33,9 @@ struct cdx_ctx {
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
   void* d_stage[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;
+  void* h_pinned[2] = {nullptr, nullptr};   // pinned read buffers of cdx_slot_commit_file
+  size_t pinned_bytes = 0;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
   uint64_t launches = 0;
   bool plain_loads = false;            // CODEX_COMMIT_PLAIN_LOADS=1: per-thread global loads instead of the TMA-staged rows (A/B only)
   char err[256] = {0};
@@ -121,6 +128,7 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
@@ -136,6 +144,8 @@ extern "C" void cdx_ctx_destroy(cdx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (int i = 0; i < 2; ++i) {
     if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
   }
@@ -651,6 +661,107 @@ extern "C" int cdx_slot_commit_range_host(cdx_ctx* ctx, const uint8_t* data, siz
   return commit_host_range(ctx, data, n_local_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, false, out);
 }
 
+// File-resident slot.  Three overlapped stages: parallel pread into one of two pinned chunks (host threads), H2D of that
+// chunk into the current device tile (copy stream), cell sponge per finished tile (alternating compute streams).
+extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t offset, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
+  if (!ctx || !path || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  *out = nullptr;
+  int rc = check_shape(ctx, n_bytes, cell_size, block_size);
+  if (rc) return rc;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(ctx, CDX_ERR_ARG, "cannot open slot data file `%s`", path);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n_blocks = n_bytes / block_size;
+  const size_t chunk_bytes_target = (size_t)64 << 20;                       // pinned chunk
+  size_t chunk_blocks = chunk_bytes_target / block_size ? chunk_bytes_target / block_size : 1;
+  size_t tile_blocks = 4 * chunk_blocks;                                    // device tile = 4 chunks = 256 MiB (one sponge wave)
+  if (tile_blocks > n_blocks) tile_blocks = n_blocks;
+  if (chunk_blocks > tile_blocks) chunk_blocks = tile_blocks;
+  const size_t chunk_bytes = chunk_blocks * block_size, tile_bytes = tile_blocks * block_size;
+  auto cleanup_fd = [&]() { close(fd); };
+  if (ctx->pinned_bytes < chunk_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
+      ctx->h_pinned[i] = nullptr;
+    }
+    ctx->pinned_bytes = 0;
+    for (int i = 0; i < 2; ++i)
+      if (cudaHostAlloc(&ctx->h_pinned[i], chunk_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cleanup_fd();
+        return fail(ctx, CDX_ERR_ALLOC, "cudaHostAlloc of %zu bytes failed", chunk_bytes);
+      }
+    ctx->pinned_bytes = chunk_bytes;
+  }
+  rc = ensure_stage(ctx, tile_bytes);
+  if (rc) { cleanup_fd(); return rc; }
+  cdx_slot* s = nullptr;
+  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, 0, n_blocks, 0, ctx->stream, &s);
+  if (rc) { cleanup_fd(); return rc; }
+  const size_t cpb = block_size / cell_size;
+  auto read_chunk_parallel = [&](uint8_t* dst, uint64_t file_off, size_t len) {
+    const unsigned n_thr = 4;
+    std::vector<std::thread> thr;
+    for (unsigned t = 0; t < n_thr; ++t) {
+      const size_t a = len * t / n_thr, b = len * (t + 1) / n_thr;
+      thr.emplace_back([=]() {
+        size_t pos = a;
+        while (pos < b) {
+          const ssize_t got = pread(fd, dst + pos, b - pos, (off_t)(file_off + pos));
+          if (got <= 0) break;                                              // EOF or error: the rest reads as zeros
+          pos += (size_t)got;
+        }
+        if (pos < b) memset(dst + pos, 0, b - pos);
+      });
+    }
+    for (auto& t : thr) t.join();
+  };
+  auto body = [&]() -> int {
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
+    size_t done_blocks = 0, chunk_no = 0;
+    for (int t = 0; done_blocks < n_blocks; ++t) {
+      const int b = t & 1;
+      cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
+      const size_t nb = n_blocks - done_blocks < tile_blocks ? n_blocks - done_blocks : tile_blocks;
+      if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));   // device tile b free again
+      for (size_t cb = 0; cb < nb; cb += chunk_blocks, ++chunk_no) {
+        const int pb = (int)(chunk_no & 1);
+        const size_t cnb = nb - cb < chunk_blocks ? nb - cb : chunk_blocks;
+        if (chunk_no >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_h2d[pb]));                  // pinned chunk pb drained
+        read_chunk_parallel((uint8_t*)ctx->h_pinned[pb], offset + (uint64_t)(done_blocks + cb) * block_size, cnb * block_size);
+        CU_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->d_stage[b] + cb * block_size, ctx->h_pinned[pb], cnb * block_size, cudaMemcpyHostToDevice,
+                                    ctx->copy_stream));
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_h2d[pb], ctx->copy_stream));
+      }
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+      CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
+      int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, s->forest[0] + 32 * done_blocks * cpb, cs);
+      if (hr) return hr;
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], cs));
+      done_blocks += nb;
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    int r = build_local_trees(s);
+    if (r) return r;
+    r = build_top(s, s->low[0], true);
+    if (r) return r;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDX_OK;
+  };
+  rc = body();
+  cleanup_fd();
+  if (rc) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamSynchronize(ctx->stream);
+    cdx_slot_free(s);
+    return rc;
+  }
+  *out = s;
+  return CDX_OK;
+}
+
 extern "C" int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells, size_t cell_size, size_t block_size, cdx_slot** out) {
   if (!ctx || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
   *out = nullptr;
@@ -669,6 +780,103 @@ extern "C" int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells,
   if (e != cudaSuccess) {
     cdx_slot_free(s);
     return fail(ctx, CDX_ERR_CUDA, "fake slot commit failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return CDX_OK;
+}
+
+// ---- persisted commitments ------------------------------------------------------------------------------------
+struct SlotImageHeader {
+  char magic[8];              // "CDXSLOT1"
+  uint64_t cell_size, block_size, n_blocks, forest_nodes, top_nodes;
+  uint32_t block_depth, slot_depth;
+};
+
+static size_t forest_node_count(const cdx_slot* s) {
+  const uint64_t cpb = s->block_size / s->cell_size;
+  size_t n = 0;
+  for (uint32_t l = 0; l <= s->block_depth; ++l) n += cpb == 1 ? s->n_local_cells : (s->n_local_cells >> l);
+  return n;
+}
+static size_t top_node_count(const cdx_slot* s) {   // slot levels 1..depth (level 0 is the forest's last layer)
+  size_t n = 0;
+  for (uint32_t l = 1; l <= s->slot_depth; ++l) n += s->width[l];
+  return n;
+}
+static bool exportable(const cdx_slot* s) { return s && s->has_top && s->top_level == 0 && s->first_block == 0 && s->n_local_blocks == s->n_total_blocks; }
+
+extern "C" size_t cdx_slot_export_size(const cdx_slot* s) {
+  return exportable(s) ? sizeof(SlotImageHeader) + 32 * (forest_node_count(s) + top_node_count(s)) : 0;
+}
+
+extern "C" int cdx_slot_export(const cdx_slot* s, uint8_t* image, size_t image_bytes) {
+  if (!s || !image) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  if (!exportable(s)) return fail(ctx, CDX_ERR_STATE, "only whole slots with their top tree can be exported");
+  if (image_bytes < cdx_slot_export_size(s)) return fail(ctx, CDX_ERR_SIZE, "image buffer too small");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  SlotImageHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, "CDXSLOT1", 8);
+  h.cell_size = s->cell_size;
+  h.block_size = s->block_size;
+  h.n_blocks = s->n_total_blocks;
+  h.forest_nodes = forest_node_count(s);
+  h.top_nodes = top_node_count(s);
+  h.block_depth = s->block_depth;
+  h.slot_depth = s->slot_depth;
+  memcpy(image, &h, sizeof h);
+  uint8_t* p = image + sizeof h;
+  CU_TRY(ctx, cudaMemcpyAsync(p, s->d_forest, 32 * h.forest_nodes, cudaMemcpyDeviceToHost, s->stream));
+  p += 32 * h.forest_nodes;
+  for (uint32_t l = 1; l <= s->slot_depth; ++l) {
+    CU_TRY(ctx, cudaMemcpyAsync(p, s->top[l], 32 * s->width[l], cudaMemcpyDeviceToHost, s->stream));
+    p += 32 * s->width[l];
+  }
+  CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+  return CDX_OK;
+}
+
+extern "C" int cdx_slot_import(cdx_ctx* ctx, const uint8_t* image, size_t image_bytes, cdx_slot** out) {
+  if (!ctx || !image || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  *out = nullptr;
+  SlotImageHeader h;
+  if (image_bytes < sizeof h) return fail(ctx, CDX_ERR_SIZE, "image too small");
+  memcpy(&h, image, sizeof h);
+  if (memcmp(h.magic, "CDXSLOT1", 8) != 0) return fail(ctx, CDX_ERR_ARG, "not a slot image");
+  int rc = check_shape(ctx, h.n_blocks * h.block_size, h.cell_size, h.block_size);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cdx_slot* s = nullptr;
+  rc = slot_alloc(ctx, h.n_blocks, h.cell_size, h.block_size, 0, h.n_blocks, 0, ctx->stream, &s);
+  if (rc) return rc;
+  auto body = [&]() -> int {
+    if (forest_node_count(s) != h.forest_nodes || s->block_depth != h.block_depth || s->slot_depth != h.slot_depth)
+      return fail(ctx, CDX_ERR_ARG, "slot image header is inconsistent with its geometry");
+    size_t top_nodes = 0;
+    for (uint32_t l = 1; l <= s->slot_depth; ++l) top_nodes += s->width[l];
+    if (top_nodes != h.top_nodes || image_bytes != sizeof h + 32 * (h.forest_nodes + h.top_nodes)) return fail(ctx, CDX_ERR_SIZE, "slot image has the wrong length");
+    const uint8_t* p = image + sizeof h;
+    CU_TRY(ctx, cudaMemcpyAsync(s->d_forest, p, 32 * h.forest_nodes, cudaMemcpyHostToDevice, s->stream));
+    p += 32 * h.forest_nodes;
+    if (top_nodes) CU_TRY(ctx, cudaMallocAsync((void**)&s->d_top, 32 * top_nodes, s->stream));
+    s->top.assign(s->slot_depth + 1, nullptr);
+    s->top[0] = s->low[0];
+    size_t off = 0;
+    for (uint32_t l = 1; l <= s->slot_depth; ++l) {
+      s->top[l] = s->d_top + 32 * off;
+      off += s->width[l];
+    }
+    if (top_nodes) CU_TRY(ctx, cudaMemcpyAsync(s->d_top, p, 32 * top_nodes, cudaMemcpyHostToDevice, s->stream));
+    s->top0_alias = true;
+    s->has_top = true;
+    CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+    return CDX_OK;
+  };
+  rc = body();
+  if (rc) {
+    cdx_slot_free(s);
+    return rc;
   }
   *out = s;
   return CDX_OK;

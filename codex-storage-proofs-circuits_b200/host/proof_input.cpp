@@ -355,8 +355,9 @@ void commitSlot(Backend& be, const GlobalConfig& g, const SlotConfig& cfg, SlotH
   if (cfg.dataSrc.kind == DataSourceKind::FakeData) {
     be.check(cdx_slot_commit_fake(be.ctx(), cfg.dataSrc.seed, (size_t)cfg.nCells, (size_t)g.cellSize, (size_t)g.blockSize, &out.h), "buildSlotTree");
   } else {
-    Cell bytes = readFileRange(cfg.dataSrc.filename, 0, g.cellSize * cfg.nCells);
-    be.check(cdx_slot_commit_host(be.ctx(), bytes.data(), bytes.size(), (size_t)g.cellSize, (size_t)g.blockSize, &out.h), "buildSlotTree");
+    // straight from the file: pread -> pinned buffers -> H2D -> sponge, overlapped (short files read as zeros, slot.nim:64-65)
+    be.check(cdx_slot_commit_file(be.ctx(), cfg.dataSrc.filename.c_str(), 0, (size_t)(g.cellSize * cfg.nCells), (size_t)g.cellSize,
+                                  (size_t)g.blockSize, &out.h), "buildSlotTree");
   }
 }
 }  // namespace

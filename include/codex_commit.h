@@ -111,6 +111,13 @@ int cdx_merkle_root_host(cdx_ctx* ctx, const uint8_t* leaves, size_t n, uint8_t 
 int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out);
 int cdx_slot_commit_dev(cdx_ctx* ctx, const void* d_data, size_t n_bytes, size_t cell_size, size_t block_size, void* stream, cdx_slot** out);
 
+/* Commit a slot straight from a file: bytes [offset, offset + n_bytes) of `path` stream through pinned host buffers
+ * (parallel pread) -> H2D -> cell sponge, all three overlapped; only the hashes stay resident.  Bytes past the end of
+ * the file read as zeros, like the reference's ignored short reads.
+ * Replaces: slotLoadCellData(SlotFile) + buildSlotTreeFull -- nim/slot.nim:57-68 (one open/seek/read per 2 KiB cell),
+ * nim/dataset.nim:34-41, nim/gen_input/bn254.nim:21-30.   */
+int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t offset, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out);
+
 /* Same over the reference's fake data source, generated on the device (never crosses PCIe).
  * Replaces: slotLoadBlockData + genFakeCell -- nim/slot.nim:23-32,70-73, seed as in nim/dataset.nim:32. */
 int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells, size_t cell_size, size_t block_size, cdx_slot** out);
@@ -131,6 +138,15 @@ int cdx_slot_subtree_roots_copy_dev(const cdx_slot* slot, void* d_dst, void* str
 /* device pointer to this rank's level-top_level nodes (n_nodes * 32 bytes), for NCCL */
 const void* cdx_slot_subtree_roots_dev(const cdx_slot* slot);
 int cdx_slot_set_top_dev(cdx_slot* slot, const void* d_level_nodes, uint64_t n_level_nodes, void* stream);
+
+/* Persist / restore a commitment (a proof server answers repeated challenges from a retained
+ * commitment instead of re-hashing the slot).  The image is a small header followed by every retained layer (canonical
+ * 32-byte elements), about 3.1 % of the slot size; it is self-describing and checked on import.  Only whole
+ * (non-sharded, top tree present) slots can be exported.  The reference keeps nothing: it rebuilds the slot tree for
+ * every sample (nim/gen_input/bn254.nim:57). */
+size_t cdx_slot_export_size(const cdx_slot* slot);
+int cdx_slot_export(const cdx_slot* slot, uint8_t* image, size_t image_bytes);
+int cdx_slot_import(cdx_ctx* ctx, const uint8_t* image, size_t image_bytes, cdx_slot** out);
 
 void cdx_slot_free(cdx_slot* slot);
 

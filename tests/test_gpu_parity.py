@@ -247,6 +247,24 @@ def test_batched_root_reconstruction(ctx, orc, pyorc):
         assert ctx.reconstruct_roots(leaves, [i % 32 for i in idx], 32, bad, depth=5)[2] != block_roots[2]
 
 
+@pytest.mark.parametrize("n_cells,cell,block", [(5 * 32, 2048, 65536), (32, 2048, 65536), (8, 2048, 2048), (256, 128, 4096)])
+def test_export_import_roundtrip(ctx, pkg, n_cells, cell, block):
+    """a persisted commitment answers challenges exactly like the live one"""
+    with ctx.slot_commit_fake(31337, n_cells, cell, block) as live:
+        image = live.export()
+        root, shape = live.root, live.shape
+        idx = list(range(0, n_cells, max(1, n_cells // 7))) + [n_cells - 1]
+        paths, leaves = live.cell_paths(idx, 24)
+    with ctx.slot_import(image) as back:
+        assert back.root == root and back.shape == shape
+        assert back.cell_paths(idx, 24) == (paths, leaves)
+        assert back.export() == image
+    with pytest.raises(pkg.CodexCommitError):
+        ctx.slot_import(image[:-32])
+    with pytest.raises(pkg.CodexCommitError):
+        ctx.slot_import(b"NOTASLOT" + image[8:])
+
+
 def test_paths_errors(ctx, pkg):
     with ctx.slot_commit_fake(1, 64) as slot:
         with pytest.raises(pkg.CodexCommitError) as e:

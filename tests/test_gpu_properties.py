@@ -150,3 +150,37 @@ def test_dataset_commit_small_vs_oracle(ctx, orc, torch_mod):
     assert sorted(k for b in bins for k in b) == list(range(13))
     loads = [sum(blocks[k] for k in b) for b in bins]
     assert max(loads) <= 1.34 * sum(blocks) / 4
+
+
+def test_commit_from_file(ctx, torch_mod, tmp_path):
+    """SlotFile at speed: pread -> pinned -> H2D -> sponge; equals the resident commitment; a short file
+    reads as zeros past its end (slot.nim:64-65); offsets select a window"""
+    import time
+    torch = torch_mod
+    n = 700 * 65536                                                      # 43.75 MiB ... plus a multi-tile case below
+    d = synthetic(ctx, torch, n)
+    host = d.cpu().numpy()
+    path = str(tmp_path / "slot.dat")
+    host.tofile(path)
+    with ctx.slot_commit_dev(d.data_ptr(), n) as a, ctx.slot_commit_file(path, n) as b:
+        assert a.root == b.root
+    short = 600 * 65536 + 1234
+    host[:short].tofile(path)
+    padded = host.copy()
+    padded[short:] = 0
+    with ctx.slot_commit_host(padded) as a, ctx.slot_commit_file(path, n) as b:
+        assert a.root == b.root
+    host.tofile(path)
+    with ctx.slot_commit_dev(d.data_ptr() + 100 * 65536, 64 * 65536) as a, ctx.slot_commit_file(path, 64 * 65536, offset=100 * 65536) as b:
+        assert a.root == b.root
+    big = 9 * 1024 * 65536 + 3 * 65536                                  # 579 MiB: three device tiles, ten pinned chunks, ragged tail
+    d2 = synthetic(ctx, torch, big, seed=7)
+    path2 = str(tmp_path / "big.dat")
+    d2.cpu().numpy().tofile(path2)
+    with ctx.slot_commit_dev(d2.data_ptr(), big) as a:
+        ra = a.root
+    t0 = time.perf_counter()
+    with ctx.slot_commit_file(path2, big) as b:
+        dt = time.perf_counter() - t0
+        assert b.root == ra
+    print(f"commit_file {big / 2**20:.0f} MiB from page cache: {big / dt / 1e9:.2f} GB/s")
