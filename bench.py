@@ -54,6 +54,28 @@ def total_perms(n_blocks: int) -> int:
     return n_blocks * PERMS_PER_BLOCK + slot_tree_perms(n_blocks)
 
 
+def layout(args, world: int):
+    """(n_total_blocks, top_level, ranges, scaling) -- the same for both arms"""
+    sharded = importlib.import_module(PKG + ".sharded")
+    if args.total_gib > 0:                             # strong scaling: one slot, 2^T-aligned chunks dealt evenly
+        n_total_blocks = int(args.total_gib * (1 << 30)) // BLOCK
+        top_level, ranges = sharded.plan_block_ranges(n_total_blocks, world)
+        return n_total_blocks, top_level, ranges, "strong"
+    blocks_per_gpu = int(args.slot_gib * (1 << 30)) // BLOCK   # weak scaling: every rank holds --slot-gib of one N x larger slot
+    top_level, ranges = sharded.fixed_ranges(blocks_per_gpu, world)
+    return blocks_per_gpu * world, top_level, ranges, "weak"
+
+
+def make_config(args, world: int, n_total_blocks: int, top_level: int, ranges) -> dict:
+    per_gpu = max(c for _, c in ranges) * BLOCK
+    return {"workload": (f"single {args.total_gib:g} GiB synthetic slot split over {world} GPU(s)" if args.total_gib > 0 else
+                         f"single {args.slot_gib:g} GiB-per-GPU synthetic slot") +
+                        f" ({n_total_blocks} blocks of 64 KiB, 2048-byte cells): cell sponge + block trees + slot tree + root",
+            "bytes_per_step": n_total_blocks * BLOCK, "cell_size": CELL, "block_size": BLOCK, "seed": SEED,
+            "parallelism": "1 GPU" if world == 1 else f"{world} ranks x block-range shards, all-gather of level-{top_level} roots",
+            "l2": f"inputs ({per_gpu / 2**30:.1f} GiB per GPU) are larger than L2; no flush needed"}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # synthetic bytes on the host (numpy twin of k_fill_synthetic) for the CPU legs
 
@@ -157,13 +179,12 @@ def run_reference(args) -> None:
         dt, _ = time_oracle_commit(sample, threads)
         t += dt
     gbs = sample * args.steps / t / 1e9
-    n_blocks_full = int(args.slot_gib * (1 << 30)) // BLOCK * args.gpus
+    n_total_blocks, top_level, ranges, scaling = layout(args, args.gpus)
     line = {
         "impl": "reference", "metric": "slot commit GB/s (with Poseidon2 perms/s)", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "u64x4 (BN254 Fr, Montgomery)", "data": "synthetic",
-        "config": {"workload": f"single {args.slot_gib:g} GiB-per-GPU synthetic slot ({n_blocks_full} blocks): cell sponge + block trees + slot root",
-                   "cell_size": CELL, "block_size": BLOCK},
+        "config": make_config(args, args.gpus, n_total_blocks, top_level, ranges),
         "perms_per_s": total_perms(sample // BLOCK) * args.steps / t,
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": f"first {args.ref_sample_mib} MiB of the workload's synthetic slot per step, {threads} threads over blocks; "
@@ -211,15 +232,7 @@ def main() -> None:
     ctx = pkg.Context(local_rank)                      # raises if libcodexcommit.so or the GPU is missing: no fallback
     stream = torch.cuda.ExternalStream(ctx.stream)     # the library's compute stream, so events see its kernels
 
-    if args.total_gib > 0:                             # strong scaling: one slot, 2^T-aligned chunks dealt evenly
-        n_total_blocks = int(args.total_gib * (1 << 30)) // BLOCK
-        top_level, ranges = sharded.plan_block_ranges(n_total_blocks, world)
-        scaling = "strong"
-    else:                                              # weak scaling: every rank holds --slot-gib of one N x larger slot
-        blocks_per_gpu = int(args.slot_gib * (1 << 30)) // BLOCK
-        n_total_blocks = blocks_per_gpu * world
-        top_level, ranges = sharded.fixed_ranges(blocks_per_gpu, world)
-        scaling = "weak"
+    n_total_blocks, top_level, ranges, scaling = layout(args, world)
     first_block, my_blocks = ranges[rank]
     n_bytes = my_blocks * BLOCK
 
@@ -304,7 +317,8 @@ def main() -> None:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = n_cells * (CELL + 32)
     roofline = {
-        "kernel": "k_hash_cells", "bound": "int32_imad (FMA-heavy pipe: IMAD.WIDE.U32 issue; neither hbm nor tensor)",
+        "kernel": "k_hash_cells_tma", "bound": "imad",
+        "bound_note": "FMA-heavy pipe: IMAD.WIDE.U32 issue rate; neither hbm nor tensor (see the hbm sub-object and DESIGN.md section 4)",
         "achieved": achieved / 1e12, "peak": imad_wide / 1e12, "unit": "T int-multiply instr/s", "frac": achieved / imad_wide,
         "peak_source": "best IMAD.WIDE.U32 rate measured in this run by cdx_probe_imad_rate (max of the no-carry and the carry-chain form); "
                        "MEASURED_PEAKS.json has no integer peak",
@@ -389,12 +403,7 @@ def main() -> None:
             "metric": "slot commit GB/s (with Poseidon2 perms/s)", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "u32x8 (BN254 Fr, 256-bit Montgomery integers)", "data": "synthetic",
-            "config": {"workload": (f"single {args.total_gib:g} GiB synthetic slot split over {world} GPU(s)" if args.total_gib > 0 else
-                                    f"single {args.slot_gib:g} GiB-per-GPU synthetic slot") +
-                                   f" ({n_total_blocks} blocks of 64 KiB, 2048-byte cells): cell sponge + block trees + slot tree + root",
-                       "bytes_per_step": total_bytes, "cell_size": CELL, "block_size": BLOCK, "seed": SEED,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} ranks x block-range shards, all-gather of level-{top_level} roots",
-                       "l2": f"inputs ({n_bytes / 2**30:.1f} GiB per GPU) are larger than L2; no flush needed"},
+            "config": make_config(args, world, n_total_blocks, top_level, ranges),
             "perms_per_s": perms_step * args.steps / ev_s, "perms_per_step": perms_step,
             "slot_root": hex(root), "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
