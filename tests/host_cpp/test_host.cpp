@@ -1,0 +1,113 @@
+// Unit tests of the C++ host mirror of reference/nim/proof_input (host/proof_input.hpp) over the CUDA backend.
+// Built and run by tests/test_gpu_host_cpp.py on a GPU box; every hash below is computed by libcodexcommit.so.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../codex-storage-proofs-circuits_b200/host/proof_input.hpp"
+
+using namespace codex;
+
+static int failures = 0;
+#define CHECK(cond)                                                         \
+  do {                                                                      \
+    if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } \
+  } while (0)
+template <class Fn> static bool throws(Fn fn) {
+  try { fn(); } catch (const AssertionDefect&) { return true; }
+  return false;
+}
+static F felt(uint64_t v) { return intToBN254((int64_t)v); }
+
+int main() {
+  // ---- pure host helpers (no hashing) ----
+  CHECK(toDecimalF(felt(0)) == "0");
+  CHECK(toDecimalF(felt(1234567)) == "1234567");
+  CHECK(toQuotedDecimalF(felt(42)) == "\"42\"");
+  CHECK(toDecimalF(intToBN254(-5)) == "21888242871839275222246405745257275088548364400416034343698204186575808495612");   // r - 5
+  CHECK(ceilingLog2(0) == -1 && ceilingLog2(1) == 0 && ceilingLog2(256) == 8 && ceilingLog2(257) == 9 && floorLog2(255) == 7);
+  CHECK(exactLog2(32) == 5 && throws([] { exactLog2(33); }) && throws([] { checkPowerOfTwo(1000, "nCells"); }));
+  CHECK(parseField("BN254") == FieldSelect::BN254 && parseField("goldilocks") == FieldSelect::Goldilocks && throws([] { parseField("bls"); }));
+  CHECK(throws([] { toFieldHashCombo(FieldSelect::BN254, HashSelect::Monolith); }));
+  GlobalConfig g;
+  CHECK(cellsPerBlock(g) == 32);
+  g.blockSize = 3000;
+  CHECK(throws([&] { cellsPerBlock(g); }));
+  g = GlobalConfig();
+  {
+    std::vector<uint8_t> b62(62, 0xff);
+    auto e = elements(b62);                       // 31k bytes -> k+1 elements (Slot.hs:243-250)
+    CHECK(e.size() == 3 && e[2][0] == 1 && e[2][1] == 0 && e[0][30] == 0xff && e[0][31] == 0);
+    CHECK(elements(std::vector<uint8_t>()).size() == 1 && elements(std::vector<uint8_t>(2048, 7)).size() == 67);
+  }
+  CHECK(extractLowBits(felt(0xabcdef), 8) == 0xef && extractLowBits(felt(0xabcdef), 64) == 0xabcdef);
+  CHECK(parametricSlotSeed(12345, 3) == 12345 + 72 + 3003);
+
+  // ---- over the GPU backend ----
+  Backend be(0);
+  HashConfig h;
+  h.field = FieldSelect::BN254;
+  h.combo = toFieldHashCombo(h.field, h.hashFun);
+  const CompressWithKey cwk = [&be](int key, const F& x, const F& y) { return compressWithKey(be, key, x, y); };
+  // Merkle.hs:136-152 testAllMerkleProofs: every leaf of trees with 1..12 leaves
+  for (int n = 1; n <= 12; ++n) {
+    std::vector<F> leaves;
+    for (int i = 1; i <= n; ++i) leaves.push_back(felt(1000 + i));
+    const MerkleTree t = merkleTree(be, h, leaves);
+    CHECK(treeNumberOfLeaves(t) == n && treeRoot(t) == merkleDigestBN254(be, leaves));
+    CHECK(treeDepth(t) == (n == 1 ? 1 : ceilingLog2(n)));
+    for (int j = 0; j < n; ++j) {
+      const MerkleProof p = merkleProof(t, j);
+      CHECK(checkMerkleProof(cwk, treeRoot(t), p));
+      if ((j ^ 1) >= n) CHECK(p.merklePath[0] == F{});          // out-of-range sibling is zero (merkle.nim:34)
+      const MerkleProof padded = padMerkleProof(p, 8);
+      CHECK(padded.merklePath.size() == 8 && padded.merklePath[7] == F{});
+    }
+    CHECK(throws([&] { merkleProof(t, n); }));
+  }
+  CHECK(compressWithKey(be, 3, felt(5), F{}) == treeRoot(merkleTree(be, h, {felt(5)})));   // singleton = one key-3 compression
+  CHECK(throws([&] { compressWithKey(be, 4, felt(1), felt(2)); }));
+  // hashCell size assertion (blocks/bn254.nim:26) and block tree == tree over cell hashes
+  CHECK(throws([&] { hashCell(be, h, g, Cell(100, 0)); }));
+  {
+    SlotConfig sc;
+    sc.nCells = 64;
+    sc.dataSrc.seed = 777;
+    const Block blk = slotLoadBlockData(be, g, sc, 1);
+    CHECK((int64_t)blk.size() == g.blockSize);
+    std::vector<Hash> ch;
+    for (int c = 0; c < 32; ++c) ch.push_back(hashCell(be, h, g, slotLoadCellData(be, g, sc, 32 + c)));
+    const MerkleTree bt = networkBlockTree(be, h, g, blk);
+    CHECK(bt.layers[0] == ch && treeRoot(bt) == hashNetworkBlock(be, h, g, blk) && treeDepth(bt) == 5);
+    // merge of a bottom and a top proof, and the mismatch assertion (merkle.nim:86-100)
+    const MerkleTree top = merkleTree(be, h, {felt(9), treeRoot(bt), felt(11)});
+    const MerkleProof merged = mergeMerkleProofs(cwk, merkleProof(bt, 7), merkleProof(top, 1));
+    CHECK(merged.leafIndex == 32 + 7 && merged.numberOfLeaves == 96 && merged.merklePath.size() == 5 + 2);
+    CHECK(throws([&] { mergeMerkleProofs(cwk, merkleProof(bt, 7), merkleProof(top, 0)); }));
+  }
+  // sampling: counters run 1..n, power-of-two assertion (sample/bn254.nim:16-27)
+  {
+    const auto idx = cellIndices(be, h, felt(1234567), felt(99), 2048, 5);
+    CHECK(idx.size() == 5 && cellIndex(be, h, felt(1234567), felt(99), 2048, 3) == idx[2]);
+    for (auto i : idx) CHECK(i >= 0 && i < 2048);
+    CHECK(throws([&] { cellIndices(be, h, felt(1), felt(2), 1000, 5); }));
+  }
+  // generateProofInputBN254 argument checks (gen_input/bn254.nim:38-39, dataset.nim:46)
+  {
+    DataSetConfig d;
+    d.nCells = 64;
+    d.nSlots = 3;
+    CHECK(throws([&] { generateProofInputBN254(be, h, g, d, 5, felt(1)); }));
+    d.nCells = 48;                                   // not a multiple of 32 cells per block
+    CHECK(throws([&] { generateProofInputBN254(be, h, g, d, 0, felt(1)); }));
+    d.nCells = 64;
+    const SlotProofInput in = generateProofInputBN254(be, h, g, d, 2, felt(1234567));
+    CHECK(in.proofInputs.size() == 5 && in.slotProof.merklePath.size() == 8 && in.nCells == 64 && in.nSlots == 3);
+    for (const auto& p : in.proofInputs) CHECK(p.merkleProof.merklePath.size() == 32 && (int64_t)p.cellData.size() == g.cellSize);
+    const std::string js = proofInputToJson(in);
+    CHECK(js.rfind("{\n  \"dataSetRoot\":      \"", 0) == 0 && js.find(", \"nSlotsPerDataSet\": 3\n") != std::string::npos);
+  }
+  std::printf(failures ? "%d FAILURES\n" : "host mirror: all checks passed\n", failures);
+  return failures ? 1 : 0;
+}
