@@ -50,3 +50,13 @@ def ctx(pkg):
     c = pkg.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def orc_mod(orc):
+    return orc
+
+
+@pytest.fixture(scope="session")
+def pyorc_mod(pyorc):
+    return pyorc
