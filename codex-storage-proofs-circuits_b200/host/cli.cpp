@@ -18,6 +18,7 @@ struct FullConfig {            // cli.nim:37-45, defaults :47-76
   int64_t entropy = 1234567;
   std::string outFile, circomFile;
   bool verbose = false;
+  bool selfcheck = false;
   int device = 0;
 };
 
@@ -45,6 +46,7 @@ static void printHelp() {      // cli.nim:80-105
   std::puts(" -F, --field      = <field>         : the underlying field: \"bn254\" or \"goldilocks\"");
   std::puts(" -H, --hash       = <hash>          : the hash function to use: \"poseidon2\" or \"monolith\"");
   std::puts(" -G, --gpu        = <device>        : CUDA device ordinal (this backend only; default 0)");
+  std::puts("     --selfcheck                    : re-derive on the GPU everything the circuit constrains before writing (this backend only)");
   std::puts("");
   std::exit(0);
 }
@@ -87,6 +89,7 @@ static FullConfig parseCliOptions(int argc, char** argv) {   // cli.nim:109-162
     else if (is("F", "field")) cfg.hashCfg.field = parseField(value);
     else if (is("H", "hash")) cfg.hashCfg.hashFun = parseHashFun(value);
     else if (is("G", "gpu")) cfg.device = (int)parseInt(value);
+    else if (key == "selfcheck") cfg.selfcheck = true;
     else {
       std::cout << "Unknown option: " << key << "\nuse --help to get a list of options\n";
       std::exit(0);
@@ -141,6 +144,11 @@ int main(int argc, char** argv) {   // cli.nim:208-237
       Backend be(cfg.device);
       const Entropy entropy = intToBN254(cfg.entropy);
       const SlotProofInput prf = generateProofInputBN254(be, cfg.hashCfg, cfg.globCfg, cfg.dsetCfg, cfg.slotIndex, entropy);
+      if (cfg.selfcheck) {
+        std::string why;
+        if (!checkProofInputBN254(be, cfg.globCfg, prf, &why)) throw AssertionDefect("selfcheck failed: " + why);
+        std::cout << "selfcheck: the proof input satisfies every constraint the circuit re-computes\n";
+      }
       exportProofInputBN254(cfg.hashCfg, cfg.outFile, prf);
     }
     std::cout << "done\n";

@@ -432,6 +432,74 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
   return out;
 }
 
+// ---- verifier side ------------------------------------------------------------------------------------------
+
+bool checkProofInputBN254(Backend& be, const GlobalConfig& g, const SlotProofInput& prf, std::string* why) {
+  auto no = [&](const std::string& msg) {
+    if (why) *why = msg;
+    return false;
+  };
+  const int64_t cpb = cellsPerBlock(g);
+  if (prf.nCells <= 0 || prf.nCells % cpb) return no("nCellsPerSlot is not a whole number of blocks");
+  const int lg = ceilingLog2(prf.nCells);
+  if (((int64_t)1 << lg) != prf.nCells) return no("nCellsPerSlot is not a power of two");              // sample_cells.circom:114-123
+  const int64_t nblocks = prf.nCells / cpb;
+  const size_t ns = prf.proofInputs.size();
+  const int bd = cpb == 1 ? 1 : exactLog2(cpb);
+  const int sd = nblocks == 1 ? 1 : ceilingLog2(nblocks);
+  if ((int)prf.slotProof.merklePath.size() != g.maxLog2NSlots) return no("slotProof has the wrong length");
+  if (prf.slotIndex < 0 || prf.slotIndex >= prf.nSlots) return no("slotIndex out of range");
+  // 1. slot root -> dataset root
+  {
+    const int dd = prf.nSlots == 1 ? 1 : ceilingLog2(prf.nSlots);
+    if (dd > g.maxLog2NSlots) return no("nSlotsPerDataSet exceeds maxLog2NSlots");
+    const uint64_t idx = (uint64_t)prf.slotIndex;
+    F top{};
+    be.check(cdx_reconstruct_roots_host(be.ctx(), prf.slotRoot.data(), &idx, (uint64_t)prf.nSlots, prf.slotProof.merklePath[0].data(),
+                                        (size_t)g.maxLog2NSlots, (size_t)dd, 1, top.data()), "dataset path");
+    if (top != prf.dataSetRoot) return no("top root check failed");
+    for (int i = dd; i < g.maxLog2NSlots; ++i)
+      if (prf.slotProof.merklePath[(size_t)i] != F{}) return no("slotProof is not zero-padded");
+  }
+  if (ns == 0) return true;
+  // 2. sampled indices
+  HashConfig h;
+  h.field = FieldSelect::BN254;
+  h.combo = FieldHashCombo::BN254_Poseidon2;
+  const std::vector<int64_t> idx = cellIndices(be, h, prf.entropy, prf.slotRoot, prf.nCells, (int64_t)ns);
+  // 3. cell hashes from the cell data (as field elements, exactly what the circuit is given)
+  std::vector<F> leaves(ns);
+  {
+    std::vector<uint8_t> cells;
+    for (const auto& p : prf.proofInputs) {
+      if ((int64_t)p.cellData.size() != g.cellSize) return no("cell data has the wrong size");
+      cells.insert(cells.end(), p.cellData.begin(), p.cellData.end());
+    }
+    be.check(cdx_hash_bytes_batch_host(be.ctx(), cells.data(), ns, (size_t)g.cellSize, leaves[0].data()), "cell hashes");
+  }
+  // 4./5. block-level, then slot-level reconstruction
+  std::vector<F> paths(ns * (size_t)g.maxDepth), blockRoots(ns), slotRoots(ns);
+  std::vector<uint64_t> within(ns), block(ns);
+  for (size_t s = 0; s < ns; ++s) {
+    const MerkleProof& mp = prf.proofInputs[s].merkleProof;
+    if ((int)mp.merklePath.size() != g.maxDepth || bd + sd > g.maxDepth) return no("merkle path has the wrong length");
+    if (mp.leafIndex != idx[s]) return no("sample " + std::to_string(s) + ": cell index does not match H(entropy | slotRoot | counter)");
+    if (mp.leafValue != leaves[s]) return no("sample " + std::to_string(s) + ": leaf value is not the hash of the cell data");
+    std::copy(mp.merklePath.begin(), mp.merklePath.end(), paths.begin() + s * (size_t)g.maxDepth);
+    within[s] = (uint64_t)(idx[s] % cpb);
+    block[s] = (uint64_t)(idx[s] / cpb);
+    for (int i = bd + sd; i < g.maxDepth; ++i)
+      if (mp.merklePath[(size_t)i] != F{}) return no("sample " + std::to_string(s) + ": merkle path is not zero-padded");
+  }
+  be.check(cdx_reconstruct_roots_host(be.ctx(), leaves[0].data(), within.data(), (uint64_t)cpb, paths[0].data(), (size_t)g.maxDepth, (size_t)bd, ns,
+                                      blockRoots[0].data()), "block-level reconstruction");
+  be.check(cdx_reconstruct_roots_host(be.ctx(), blockRoots[0].data(), block.data(), (uint64_t)nblocks, paths[(size_t)bd].data(), (size_t)g.maxDepth,
+                                      (size_t)sd, ns, slotRoots[0].data()), "slot-level reconstruction");
+  for (size_t s = 0; s < ns; ++s)
+    if (slotRoots[s] != prf.slotRoot) return no("sample " + std::to_string(s) + ": middle/bottom root check failed");
+  return true;
+}
+
 // ---- nim/json/bn254.nim, nim/json/shared.nim ----------------------------------------------------------------
 
 namespace {

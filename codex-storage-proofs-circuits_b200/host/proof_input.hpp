@@ -127,4 +127,12 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& h, const G
 void exportProofInputBN254(const HashConfig& h, const std::string& fname, const SlotProofInput& prf);    // json/bn254.nim:77-79
 std::string proofInputToJson(const SlotProofInput& prf);                                                 // the text exportProofInput writes (:57-74)
 
+// ---- verifier side (what the circuit re-computes) ---------------------------------------
+// Re-derives everything the SampleAndProve circuit constrains, on the GPU, in five batched launches: the dataset path
+// (circuit/codex/sample_cells.circom:95-109), the sampled indices (:23-48,125-147), every cell hash from its 67 field
+// elements, the block-level and then the slot-level root of every sample (circuit/codex/single_cell.circom:41-71 --
+// two stages, each restarting with the bottom-layer key).  Returns true if the input would satisfy the circuit;
+// otherwise false with the first failed check in *why.
+bool checkProofInputBN254(Backend& be, const GlobalConfig& g, const SlotProofInput& prf, std::string* why = nullptr);
+
 }  // namespace codex

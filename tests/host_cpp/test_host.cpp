@@ -105,6 +105,26 @@ int main() {
     const SlotProofInput in = generateProofInputBN254(be, h, g, d, 2, felt(1234567));
     CHECK(in.proofInputs.size() == 5 && in.slotProof.merklePath.size() == 8 && in.nCells == 64 && in.nSlots == 3);
     for (const auto& p : in.proofInputs) CHECK(p.merkleProof.merklePath.size() == 32 && (int64_t)p.cellData.size() == g.cellSize);
+    // verifier side: accepts the generated input, pinpoints tampering
+    std::string why;
+    CHECK(checkProofInputBN254(be, g, in, &why));
+    {
+      SlotProofInput bad = in;
+      bad.proofInputs[1].merkleProof.merklePath[2][0] ^= 1;
+      CHECK(!checkProofInputBN254(be, g, bad, &why) && why.find("sample 1") != std::string::npos);
+      bad = in;
+      bad.proofInputs[3].cellData[100] ^= 0x80;
+      CHECK(!checkProofInputBN254(be, g, bad, &why) && why.find("sample 3: leaf value") != std::string::npos);
+      bad = in;
+      bad.dataSetRoot[5] ^= 1;
+      CHECK(!checkProofInputBN254(be, g, bad, &why) && why == "top root check failed");
+      bad = in;
+      bad.entropy[0] ^= 1;
+      CHECK(!checkProofInputBN254(be, g, bad, &why) && why.find("cell index") != std::string::npos);
+      bad = in;
+      bad.slotProof.merklePath[7][0] = 9;
+      CHECK(!checkProofInputBN254(be, g, bad, &why) && why == "slotProof is not zero-padded");
+    }
     const std::string js = proofInputToJson(in);
     CHECK(js.rfind("{\n  \"dataSetRoot\":      \"", 0) == 0 && js.find(", \"nSlotsPerDataSet\": 3\n") != std::string::npos);
   }

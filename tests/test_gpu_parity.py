@@ -348,6 +348,14 @@ def test_cli_slot_file_source(tmp_path, ctx):
     cv.verify_input_json(a, 32, 8, 2048, 65536)
 
 
+def test_cli_selfcheck(tmp_path):
+    res, out = run_cli("--field=bn254 --ncells=512 --nslots=13 --index=7 --nsamples=20 --seed=666 --selfcheck".split(), tmp_path)
+    assert res.returncode == 0, res.stderr
+    assert "selfcheck: the proof input satisfies every constraint" in res.stdout
+    from oracle import circuit_verifier as cv
+    cv.verify_input_json(open(out).read(), 32, 8, 2048, 65536)
+
+
 def test_cli_error_behaviour(tmp_path):
     res, _ = run_cli(["--field=bn254", "--ncells=1000"], tmp_path)           # checkPowerOfTwo (cli.nim:143, misc.nim:29-32)
     assert res.returncode != 0 and "expected to be a power of 2" in res.stderr
