@@ -219,6 +219,8 @@ def main() -> None:
 
     import torch
     import torch.distributed as dist
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        importlib.import_module(PKG + ".build").ensure_built()   # no-op when the in-tree build exists
     pkg = importlib.import_module(PKG)
     sharded = importlib.import_module(PKG + ".sharded")
 

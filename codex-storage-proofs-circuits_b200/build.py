@@ -63,6 +63,15 @@ def build_host(force: bool = False) -> str:
     return CLI
 
 
+def ensure_built() -> None:
+    """Build the CUDA library / host cli only if the artefact is MISSING (fresh checkout on a box with nvcc); an existing
+    build is never replaced behind the caller's back.  This is not a fallback: it produces the same sm_100a library."""
+    if not os.path.exists(LIB):
+        build_library(force=True)
+    if not os.path.exists(CLI):
+        build_host(force=True)
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -21,6 +21,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def pkg():
+    importlib.import_module(PKG + ".build").ensure_built()      # no-op when the in-tree build exists
     return importlib.import_module(PKG)
 
 
