@@ -219,8 +219,13 @@ def main() -> None:
 
     import torch
     import torch.distributed as dist
+    build_mod = importlib.import_module(PKG + ".build")
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        importlib.import_module(PKG + ".build").ensure_built()   # no-op when the in-tree build exists
+        build_mod.ensure_built()                                 # no-op when the in-tree build exists
+    else:
+        t_wait = time.time()
+        while not os.path.exists(build_mod.LIB) and time.time() - t_wait < 600:
+            time.sleep(1.0)
     pkg = importlib.import_module(PKG)
     sharded = importlib.import_module(PKG + ".sharded")
 
