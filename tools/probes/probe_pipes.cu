@@ -114,6 +114,89 @@ __global__ void k_dfma(uint32_t seed, uint32_t* sink) {
   if (acc == 0.123) sink[0] = 1;
 }
 
+
+// 9: co-issue, same thread: 16 IMAD.WIDE-class ops (two X chains of 4 wide pairs) + n_dfma DFMAs per unroll step
+template <int NDFMA>
+__global__ void k_mix_thread(uint32_t seed, uint32_t* sink) { DECL
+  double x = 1.0 + 1e-9 * (seed + threadIdx.x), y = 1.0 - 1e-9 * blockIdx.x;
+  double d0 = x, d1 = y, d2 = x + 1, d3 = y + 1, d4 = x + 2, d5 = y + 2, d6 = x + 3, d7 = y + 3;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      asm volatile(
+        "mad.lo.cc.u32 %0,%16,%17,%0; madc.hi.cc.u32 %8,%16,%17,%8; madc.lo.cc.u32 %1,%16,%17,%1; madc.hi.cc.u32 %9,%16,%17,%9;\n\t"
+        "madc.lo.cc.u32 %2,%16,%17,%2; madc.hi.cc.u32 %10,%16,%17,%10; madc.lo.cc.u32 %3,%16,%17,%3; madc.hi.u32 %11,%16,%17,%11;\n\t"
+        "mad.lo.cc.u32 %4,%16,%17,%4; madc.hi.cc.u32 %12,%16,%17,%12; madc.lo.cc.u32 %5,%16,%17,%5; madc.hi.cc.u32 %13,%16,%17,%13;\n\t"
+        "madc.lo.cc.u32 %6,%16,%17,%6; madc.hi.cc.u32 %14,%16,%17,%14; madc.lo.cc.u32 %7,%16,%17,%7; madc.hi.u32 %15,%16,%17,%15;"
+        : REGS16 : "r"(a), "r"(b));
+#pragma unroll
+      for (int k = 0; k < NDFMA / 8; ++k)
+        asm volatile("fma.rn.f64 %0,%0,%8,%9; fma.rn.f64 %1,%1,%8,%9; fma.rn.f64 %2,%2,%8,%9; fma.rn.f64 %3,%3,%8,%9;\n\t"
+                     "fma.rn.f64 %4,%4,%8,%9; fma.rn.f64 %5,%5,%8,%9; fma.rn.f64 %6,%6,%8,%9; fma.rn.f64 %7,%7,%8,%9;"
+          : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+d"(d6), "+d"(d7) : "d"(x), "d"(y));
+    }
+  }
+  double dacc = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
+  if (dacc == 0.123) sink[1] = 1;
+  SINK }
+
+// 10: co-issue, different warps of one block: even warps run the IMAD.WIDE.X chains, odd warps run DFMA chains
+__global__ void k_mix_warps(uint32_t seed, uint32_t* sink, int imad_iters, int dfma_iters) {
+  if (((threadIdx.x >> 5) & 1) == 0) { DECL
+    for (int it = 0; it < imad_iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        asm volatile(
+          "mad.lo.cc.u32 %0,%16,%17,%0; madc.hi.cc.u32 %8,%16,%17,%8; madc.lo.cc.u32 %1,%16,%17,%1; madc.hi.cc.u32 %9,%16,%17,%9;\n\t"
+          "madc.lo.cc.u32 %2,%16,%17,%2; madc.hi.cc.u32 %10,%16,%17,%10; madc.lo.cc.u32 %3,%16,%17,%3; madc.hi.u32 %11,%16,%17,%11;\n\t"
+          "mad.lo.cc.u32 %4,%16,%17,%4; madc.hi.cc.u32 %12,%16,%17,%12; madc.lo.cc.u32 %5,%16,%17,%5; madc.hi.cc.u32 %13,%16,%17,%13;\n\t"
+          "madc.lo.cc.u32 %6,%16,%17,%6; madc.hi.cc.u32 %14,%16,%17,%14; madc.lo.cc.u32 %7,%16,%17,%7; madc.hi.u32 %15,%16,%17,%15;"
+          : REGS16 : "r"(a), "r"(b));
+    } SINK
+  } else {
+    double x = 1.0 + 1e-9 * (seed + threadIdx.x), y = 1.0 - 1e-9 * blockIdx.x;
+    double d0 = x, d1 = y, d2 = x + 1, d3 = y + 1, d4 = x + 2, d5 = y + 2, d6 = x + 3, d7 = y + 3;
+    for (int it = 0; it < dfma_iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        asm volatile("fma.rn.f64 %0,%0,%8,%9; fma.rn.f64 %1,%1,%8,%9; fma.rn.f64 %2,%2,%8,%9; fma.rn.f64 %3,%3,%8,%9;\n\t"
+                     "fma.rn.f64 %4,%4,%8,%9; fma.rn.f64 %5,%5,%8,%9; fma.rn.f64 %6,%6,%8,%9; fma.rn.f64 %7,%7,%8,%9;"
+          : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+d"(d6), "+d"(d7) : "d"(x), "d"(y));
+    }
+    double dacc = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7;
+    if (dacc == 0.123) sink[1] = 1;
+  }
+}
+
+static void run_mix_warps(int sm, int imad_iters, int dfma_iters) {
+  uint32_t* sink; cudaMalloc(&sink, 8);
+  const int blocks = sm * 8, threads = 256;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0); k_mix_warps<<<blocks, threads>>>(12345u + rep, sink, imad_iters, dfma_iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 0 && ms < best) best = ms;
+  }
+  double half = (double)blocks * threads / 2 * UNROLL;
+  double wide = half * imad_iters * 8, dfma = half * dfma_iters * 8;   // 8 wide products (16 IMAD.WIDE-class ops) / 8 DFMA per unroll step
+  printf("warps split: imad_iters %5d dfma_iters %5d  %8.3f ms   wide products %6.2f /clk/SM   DFMA %6.2f /clk/SM\n", imad_iters, dfma_iters, best,
+         wide / (best * 1e-3) / (sm * 1.965e9), dfma / (best * 1e-3) / (sm * 1.965e9));
+  cudaFree(sink);
+}
+template <class K> static void run_mix_thread(const char* name, K kernel, int sm, int ndfma) {
+  uint32_t* sink; cudaMalloc(&sink, 8);
+  const int blocks = sm * 8, threads = 256;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0); kernel<<<blocks, threads>>>(12345u + rep, sink); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 0 && ms < best) best = ms;
+  }
+  double steps = (double)blocks * threads * ITERS * UNROLL;
+  printf("%-40s %8.3f ms   wide products %6.2f /clk/SM   DFMA %6.2f /clk/SM\n", name, best, steps * 8 / (best * 1e-3) / (sm * 1.965e9), steps * ndfma / (best * 1e-3) / (sm * 1.965e9));
+  cudaFree(sink);
+}
+
 template <class K> static void run(const char* name, K kernel, int sm, double per_unroll = 8) {
   uint32_t* sink; cudaMalloc(&sink, 4);
   const int blocks = sm * 8, threads = 256;
@@ -137,5 +220,16 @@ int main() {
   run("IMAD.WIDE.U32.X carry chains of 4", k_wide_x_chain4, sm);
   run("IADD3 / IADD3.X carry chains (ALU pipe)", k_alu_carry, sm, 16);
   run("DFMA (fp64 pipe)", k_dfma, sm);
+  printf("-- co-issue of the FMA-heavy integer pipe and the fp64 pipe --\n");
+  run_mix_thread("same thread: 8 wide.X pairs + 0 DFMA", k_mix_thread<0>, sm, 0);
+  run_mix_thread("same thread: 8 wide.X pairs + 8 DFMA", k_mix_thread<8>, sm, 8);
+  run_mix_thread("same thread: 8 wide.X pairs + 16 DFMA", k_mix_thread<16>, sm, 16);
+  run_mix_thread("same thread: 8 wide.X pairs + 24 DFMA", k_mix_thread<24>, sm, 24);
+  run_mix_warps(sm, ITERS, 0);
+  run_mix_warps(sm, 0, ITERS);
+  run_mix_warps(sm, 0, 2 * ITERS);
+  run_mix_warps(sm, ITERS, ITERS);
+  run_mix_warps(sm, ITERS, 2 * ITERS);
+  run_mix_warps(sm, ITERS, 3 * ITERS);
   return 0;
 }
