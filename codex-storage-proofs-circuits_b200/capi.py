@@ -55,6 +55,7 @@ SYMBOLS = {
     "cdx_slot_shape": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32), C.POINTER(_u32)]),
     "cdx_slot_read_layer": (_int, [_vp, _int, _u32, _u64, _u64, _vp]),
     "cdx_slot_cell_paths": (_int, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "cdx_slot_prove_batch": (_int, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp]),
     "cdx_reconstruct_roots_host": (_int, [_vp, _vp, _vp, _u64, _vp, _sz, _sz, _sz, _vp]),
     "cdx_cell_indices": (_int, [_vp, _vp, _vp, _u64, _sz, _vp]),
     "cdx_fake_cells_host": (_int, [_vp, _u64, _u64, _sz, _sz, _vp]),
@@ -355,6 +356,24 @@ class Slot:
         self.ctx._chk(self.ctx.lib.cdx_slot_cell_paths(self.h, C.addressof(idx), n, max_depth, C.addressof(out), C.addressof(leaf)))
         flat = unpack(out.raw[:32 * n * max_depth])
         return [flat[i * max_depth:(i + 1) * max_depth] for i in range(n)], unpack(leaf.raw[:32 * n])
+
+    def prove_batch(self, entropies: Sequence[int], n_samples: int, max_depth: int):
+        """answer many challenges at once: -> (indices[k][c], paths[k][c][level], leaves[k][c])"""
+        k = len(entropies)
+        total = k * n_samples
+        ent = b"".join(f2b(e) for e in entropies)
+        idx = (C.c_uint64 * max(total, 1))()
+        out = C.create_string_buffer(32 * total * max_depth if total else 1)
+        leaf = C.create_string_buffer(32 * total if total else 1)
+        self.ctx._chk(self.ctx.lib.cdx_slot_prove_batch(self.h, _addr(ent), k, n_samples, max_depth, C.addressof(idx), C.addressof(out),
+                                                        C.addressof(leaf)))
+        flat = unpack(out.raw[:32 * total * max_depth])
+        leaves = unpack(leaf.raw[:32 * total])
+        ii = list(idx)[:total]
+        paths = [flat[i * max_depth:(i + 1) * max_depth] for i in range(total)]
+        return ([ii[j * n_samples:(j + 1) * n_samples] for j in range(k)],
+                [paths[j * n_samples:(j + 1) * n_samples] for j in range(k)],
+                [leaves[j * n_samples:(j + 1) * n_samples] for j in range(k)])
 
     def export(self) -> bytes:
         n = self.ctx.lib.cdx_slot_export_size(self.h)

@@ -966,20 +966,7 @@ extern "C" int cdx_slot_read_layer(const cdx_slot* s, int tree, uint32_t level, 
   return CDX_OK;
 }
 
-extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indices, size_t n_samples, size_t max_depth, uint8_t* out, uint8_t* leaf_out) {
-  if (!s || !cell_indices || !out) return CDX_ERR_ARG;
-  cdx_ctx* ctx = s->ctx;
-  if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "no top tree yet");
-  if (n_samples == 0) return CDX_OK;
-  const uint64_t n_cells_total = s->n_total_blocks << s->cpb_log2;
-  if (max_depth < s->block_depth + s->slot_depth || max_depth > 64)
-    return fail(ctx, CDX_ERR_RANGE, "max_depth %zu < path length %u (padMerkleProof)", max_depth, s->block_depth + s->slot_depth);
-  if (n_samples > (1u << 20)) return fail(ctx, CDX_ERR_SIZE, "too many samples in one call");
-  for (size_t i = 0; i < n_samples; ++i)
-    if (cell_indices[i] >= n_cells_total) return fail(ctx, CDX_ERR_RANGE, "cell index %llu >= %llu", (unsigned long long)cell_indices[i], (unsigned long long)n_cells_total);
-  if (s->block_depth > 32 || s->slot_depth >= 40) return fail(ctx, CDX_ERR_RANGE, "tree too deep for the path plan");
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  PathPlan plan;
+static void make_path_plan(const cdx_slot* s, PathPlan& plan) {
   memset(&plan, 0, sizeof plan);
   plan.singles = (s->block_size / s->cell_size) == 1 ? 1u : 0u;
   for (uint32_t l = 0; l < s->block_depth; ++l) plan.forest[l] = s->forest[l];
@@ -998,6 +985,23 @@ extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indic
   plan.slot_depth = s->slot_depth;
   plan.top_level = s->top_level;
   plan.cells_per_block_log2 = s->cpb_log2;
+}
+
+extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indices, size_t n_samples, size_t max_depth, uint8_t* out, uint8_t* leaf_out) {
+  if (!s || !cell_indices || !out) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "no top tree yet");
+  if (n_samples == 0) return CDX_OK;
+  const uint64_t n_cells_total = s->n_total_blocks << s->cpb_log2;
+  if (max_depth < s->block_depth + s->slot_depth || max_depth > 64)
+    return fail(ctx, CDX_ERR_RANGE, "max_depth %zu < path length %u (padMerkleProof)", max_depth, s->block_depth + s->slot_depth);
+  if (n_samples > (1u << 20)) return fail(ctx, CDX_ERR_SIZE, "too many samples in one call");
+  for (size_t i = 0; i < n_samples; ++i)
+    if (cell_indices[i] >= n_cells_total) return fail(ctx, CDX_ERR_RANGE, "cell index %llu >= %llu", (unsigned long long)cell_indices[i], (unsigned long long)n_cells_total);
+  if (s->block_depth > 32 || s->slot_depth >= 40) return fail(ctx, CDX_ERR_RANGE, "tree too deep for the path plan");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  PathPlan plan;
+  make_path_plan(s, plan);
   DevBuf d_idx, d_out, d_leaf;
   CU_TRY(ctx, d_idx.alloc(8 * n_samples, s->stream));
   CU_TRY(ctx, d_out.alloc(32 * n_samples * max_depth, s->stream));
@@ -1010,6 +1014,47 @@ extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indic
   CU_TRY(ctx, cudaGetLastError());
   CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, 32 * n_samples * max_depth, cudaMemcpyDeviceToHost, s->stream));
   if (leaf_out) CU_TRY(ctx, cudaMemcpyAsync(leaf_out, d_leaf.p, 32 * n_samples, cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(s->stream));
+  return CDX_OK;
+}
+
+// Proof-server call: many challenges against one retained commitment.  Per challenge the reference
+// runs cellIndices (sample/bn254.nim:26-27) and then one merkleProof pair per sample (gen_input/bn254.nim:53-74);
+// here all challenges share three launches-worth of work: indices for every (challenge, counter) from the slot root
+// that already lives on the device, the path gather reading those indices in place, one copy back.
+extern "C" int cdx_slot_prove_batch(const cdx_slot* s, const uint8_t* entropies, size_t n_challenges, size_t n_samples, size_t max_depth,
+                                    uint64_t* indices_out, uint8_t* paths_out, uint8_t* leaves_out) {
+  if (!s || !entropies || !indices_out || !paths_out) return CDX_ERR_ARG;
+  cdx_ctx* ctx = s->ctx;
+  if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "no top tree yet");
+  const uint64_t n_cells_total = s->n_total_blocks << s->cpb_log2;
+  if (!is_pow2(n_cells_total)) return fail(ctx, CDX_ERR_NOT_POW2, "for this version, `numberOfCells` is assumed to be a power of two");
+  if (max_depth < s->block_depth + s->slot_depth || max_depth > 64)
+    return fail(ctx, CDX_ERR_RANGE, "max_depth %zu < path length %u (padMerkleProof)", max_depth, s->block_depth + s->slot_depth);
+  if (s->block_depth > 32 || s->slot_depth >= 40) return fail(ctx, CDX_ERR_RANGE, "tree too deep for the path plan");
+  if (n_challenges == 0 || n_samples == 0) return CDX_OK;
+  if (n_samples > 0xffffffffu || n_challenges > (1u << 20) || n_challenges * n_samples > (1u << 20))
+    return fail(ctx, CDX_ERR_SIZE, "too many (challenge, sample) pairs in one call");
+  const size_t total = n_challenges * n_samples;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  PathPlan plan;
+  make_path_plan(s, plan);
+  DevBuf d_ent, d_idx, d_out, d_leaf;
+  CU_TRY(ctx, d_ent.alloc(32 * n_challenges, s->stream));
+  CU_TRY(ctx, d_idx.alloc(8 * total, s->stream));
+  CU_TRY(ctx, d_out.alloc(32 * total * max_depth, s->stream));
+  CU_TRY(ctx, d_leaf.alloc(32 * total, s->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(d_ent.p, entropies, 32 * n_challenges, cudaMemcpyHostToDevice, s->stream));
+  LAUNCH(ctx, k_cell_indices, total, s->stream, d_ent.u8(), (const uint8_t*)s->top[s->slot_depth], n_cells_total - 1, (uint32_t)n_samples, total,
+         (uint64_t*)d_idx.p);
+  const size_t threads = total * (max_depth + 1) * 2;
+  k_gather_paths<<<grid_for(threads, 256), 256, 0, s->stream>>>(plan, (const uint64_t*)d_idx.p, (uint32_t)total, (uint32_t)max_depth, d_out.u8(),
+                                                               d_leaf.u8());
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaMemcpyAsync(indices_out, d_idx.p, 8 * total, cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(paths_out, d_out.p, 32 * total * max_depth, cudaMemcpyDeviceToHost, s->stream));
+  if (leaves_out) CU_TRY(ctx, cudaMemcpyAsync(leaves_out, d_leaf.p, 32 * total, cudaMemcpyDeviceToHost, s->stream));
   CU_TRY(ctx, cudaStreamSynchronize(s->stream));
   return CDX_OK;
 }
@@ -1049,7 +1094,7 @@ extern "C" int cdx_cell_indices(cdx_ctx* ctx, const uint8_t entropy[32], const u
   CU_TRY(ctx, d_out.alloc(8 * n_samples, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(d_in.p, entropy, 32, cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(d_in.u8() + 32, slot_root, 32, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(ctx, k_cell_indices, n_samples, ctx->stream, d_in.u8(), n_cells - 1, (uint32_t)n_samples, (uint64_t*)d_out.p);
+  LAUNCH(ctx, k_cell_indices, n_samples, ctx->stream, d_in.u8(), d_in.u8() + 32, n_cells - 1, (uint32_t)n_samples, n_samples, (uint64_t*)d_out.p);
   CU_TRY(ctx, cudaMemcpyAsync(indices, d_out.p, 8 * n_samples, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return CDX_OK;

@@ -277,15 +277,19 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_reconstruct_roots(const uint8_t* 
   st_felt(out + 32 * i, from_mont(h));
 }
 
-// K5: sampled cell indices.                                       sample/bn254.nim:16-27, types/bn254.nim:47-59
-__global__ void k_cell_indices(const uint8_t* __restrict__ entropy_root /* 64 B */, uint64_t mask, uint32_t n_samples,
-                               uint64_t* __restrict__ out) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_samples) return;
+// K5: sampled cell indices, one thread per (challenge, counter).   sample/bn254.nim:16-27, types/bn254.nim:47-59
+// entropies: n_challenges x 32 B, root: 32 B (both canonical), out[ch * n_samples + c-1].
+__global__ void k_cell_indices(const uint8_t* __restrict__ entropies, const uint8_t* __restrict__ root, uint64_t mask, uint32_t n_samples,
+                               size_t total, uint64_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t ch = i / n_samples;
+  const uint32_t counter = (uint32_t)(i % n_samples) + 1u;     // counters run 1..nSamples
   auto get = [&](uint32_t k) {
-    if (k < 2) return ld_felt(entropy_root + 32 * k);
+    if (k == 0) return ld_felt(entropies + 32 * ch);
+    if (k == 1) return ld_felt(root);
     Fr c = fr_zero();
-    c.l[0] = i + 1u;                                           // counters run 1..nSamples
+    c.l[0] = counter;
     return c;
   };
   Fr h = from_mont(sponge_elems(get, 3, 2));

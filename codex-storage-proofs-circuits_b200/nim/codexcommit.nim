@@ -30,6 +30,7 @@ proc cdx_slot_root*(slot: CdxSlot, rootOut: ptr byte): cint {.importc.}
 proc cdx_slot_shape*(slot: CdxSlot, nCells, nBlocks: ptr uint64, blockDepth, slotDepth: ptr uint32): cint {.importc.}
 proc cdx_slot_read_layer*(slot: CdxSlot, tree: cint, level: uint32, first, count: uint64, outp: ptr byte): cint {.importc.}
 proc cdx_slot_cell_paths*(slot: CdxSlot, cellIndices: ptr uint64, nSamples, maxDepth: csize_t, outp, leafOut: ptr byte): cint {.importc.}
+proc cdx_slot_prove_batch*(slot: CdxSlot, entropies: ptr byte, nChallenges, nSamples, maxDepth: csize_t, indicesOut: ptr uint64, pathsOut, leavesOut: ptr byte): cint {.importc.}
 proc cdx_cell_indices*(ctx: CdxCtx, entropy, slotRoot: ptr byte, nCells: uint64, nSamples: csize_t, indices: ptr uint64): cint {.importc.}
 proc cdx_fake_cells_host*(ctx: CdxCtx, seed, firstCell: uint64, nCells, cellSize: csize_t, outp: ptr byte): cint {.importc.}
 {.pop.}

@@ -168,6 +168,16 @@ int cdx_slot_read_layer(const cdx_slot* slot, int tree, uint32_t level, uint64_t
  * For a sharded slot only levels held by this rank are filled, the rest are left zero (sum over ranks = path). */
 int cdx_slot_cell_paths(const cdx_slot* slot, const uint64_t* cell_indices, size_t n_samples, size_t max_depth, uint8_t* out, uint8_t* leaf_out);
 
+/* Proof-server call: answer n_challenges challenges against one retained commitment in one pass.  For challenge k
+ * (entropies + 32 k) it produces what cdx_cell_indices followed by cdx_slot_cell_paths would: indices_out[k * n_samples
+ * + c-1], paths_out[(k * n_samples + c-1) * max_depth * 32 ...], leaves_out (may be NULL) likewise -- the indices are
+ * derived from the slot root on the device and never visit the host in between.  The slot's cell count must be a
+ * power of two (nim/sample/bn254.nim:19-20).  Replaces, per challenge: cellIndices (nim/sample/bn254.nim:26-27) and
+ * the per-sample proof loop of generateProofInput (nim/gen_input/bn254.nim:53-74), which rebuilds the slot tree for
+ * every sample (:57). */
+int cdx_slot_prove_batch(const cdx_slot* slot, const uint8_t* entropies, size_t n_challenges, size_t n_samples, size_t max_depth,
+                         uint64_t* indices_out, uint8_t* paths_out, uint8_t* leaves_out);
+
 /* Batched verifier walk: roots_out[i] = the root reconstructed from leaf i at index indices[i] in a tree of n_leaves
  * leaves along the first `depth` elements of its path (paths are n x path_stride elements, so padded paths can be
  * passed as they are).  Replaces: reconstructRoot / checkMerkleProof -- nim/merkle.nim:51-77 (also the check inside

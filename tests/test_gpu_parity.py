@@ -265,6 +265,40 @@ def test_export_import_roundtrip(ctx, pkg, n_cells, cell, block):
         ctx.slot_import(b"NOTASLOT" + image[8:])
 
 
+def test_prove_batch_many_challenges(ctx, orc, pyorc, pkg):
+    """cdx_slot_prove_batch == per challenge cellIndices (sample/bn254.nim:16-27) then merkleProof x2 / merge / pad
+    (gen_input/bn254.nim:53-74), against the oracle; and the two-stage verifier accepts every answer"""
+    seed, n_cells, n_samples, depth = 777, 8 * 32, 7, 32
+    entropies = [1234567, 0, 1, R - 1, 0xdeadbeef << 200] + [random.Random(5).getrandbits(253) for _ in range(20)]
+    with ctx.slot_commit_fake(seed, n_cells) as slot:
+        root, bh, ch = orc.commit_fake_slot(seed, n_cells, want_cells=True)
+        big = orc.merkle_layers(bh)
+        assert slot.root == root
+        idx, paths, leaves = slot.prove_batch(entropies, n_samples, depth)
+        for k, e in enumerate(entropies):
+            exp_idx = pyorc.cell_indices(e, root, n_cells, n_samples)
+            assert idx[k] == exp_idx
+            assert idx[k] == ctx.cell_indices(e, root, n_cells, n_samples)
+            for c, i in enumerate(exp_idx):
+                mini = orc.merkle_layers(ch[(i // 32) * 32:(i // 32 + 1) * 32])
+                exp = pyorc.merkle_proof(mini, i % 32).merkle_path + pyorc.merkle_proof(big, i // 32).merkle_path
+                assert paths[k][c] == exp + [0] * (depth - len(exp))
+                assert leaves[k][c] == ch[i]
+        flat_i = [i for row in idx for i in row]
+        flat_p = [p for row in paths for p in row]
+        flat_l = [v for row in leaves for v in row]
+        blocks = ctx.reconstruct_roots(flat_l, [i % 32 for i in flat_i], 32, flat_p, depth=5)
+        assert ctx.reconstruct_roots(blocks, [i // 32 for i in flat_i], 8, [p[5:] for p in flat_p], depth=3) == [root] * len(flat_i)
+        assert slot.prove_batch([], n_samples, depth) == ([], [], [])
+        with pytest.raises(pkg.CodexCommitError) as e:
+            slot.prove_batch([1], 1, 7)                            # padMerkleProof: depth too small (types.nim:29)
+        assert e.value.status == pkg.capi.CDX_ERR_RANGE
+    with ctx.slot_commit_fake(seed, 5 * 32) as ragged:             # sampling needs a power-of-two cell count (sample/bn254.nim:19-20)
+        with pytest.raises(pkg.CodexCommitError) as e:
+            ragged.prove_batch([1], 1, depth)
+        assert e.value.status == pkg.capi.CDX_ERR_NOT_POW2
+
+
 def test_paths_errors(ctx, pkg):
     with ctx.slot_commit_fake(1, 64) as slot:
         with pytest.raises(pkg.CodexCommitError) as e:
