@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <thread>
 #include <vector>
@@ -37,6 +38,7 @@ struct cdx_ctx {
   size_t pinned_bytes = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
   uint64_t launches = 0;
+  bool no_bounce = false;              // CODEX_COMMIT_NO_BOUNCE=1: pageable host slots straight through cudaMemcpyAsync (A/B only)
   bool plain_loads = false;            // CODEX_COMMIT_PLAIN_LOADS=1: per-thread global loads instead of the TMA-staged rows (A/B only)
   char err[256] = {0};
 };
@@ -112,6 +114,7 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   if (!ctx) return CDX_ERR_ALLOC;
   ctx->device = device;
   if (const char* v = getenv("CODEX_COMMIT_PLAIN_LOADS")) ctx->plain_loads = v[0] == '1';
+  if (const char* v = getenv("CODEX_COMMIT_NO_BOUNCE")) ctx->no_bounce = v[0] == '1';
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) {   // keep freed tree buffers in the pool instead of returning them to the driver
@@ -585,6 +588,10 @@ static int ensure_stage(cdx_ctx* ctx, size_t bytes) {
 
 // Host-resident slot (or block range of one): the bytes stream through two device tiles; the copy of tile t+1 (copy
 // stream) overlaps the cell sponge of tile t (compute stream).  Only hashes stay resident.
+typedef std::function<void(uint8_t* dst, uint64_t offset, size_t len)> ChunkFill;
+static int commit_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block, uint64_t n_total_blocks,
+                         int top_level, bool whole_slot, const ChunkFill& fill, cdx_slot** out);
+
 static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block,
                              uint64_t n_total_blocks, int top_level, bool whole_slot, cdx_slot** out) {
   if (!ctx || !data || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
@@ -592,6 +599,17 @@ static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   int rc = check_shape(ctx, n_bytes, cell_size, block_size);
   if (rc) return rc;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_bytes >= ((size_t)256 << 20) && !ctx->no_bounce) {
+    // Pageable memory (an ordinary malloc / Nim seq) is copied by the driver through one staging thread at ~11 GB/s,
+    // below the sponge rate; several host threads copying into our own pinned chunks keep up with it.
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, data);
+    if (e != cudaSuccess) cudaGetLastError();
+    if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) {
+      ChunkFill fill = [data](uint8_t* dst, uint64_t off, size_t len) { memcpy(dst, data + off, len); };
+      return commit_staged(ctx, n_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, whole_slot, fill, out);
+    }
+  }
   const size_t n_blocks = n_bytes / block_size;
   if (whole_slot) n_total_blocks = n_blocks;
   // Tile = 256 MiB: 131 072 cells of 2 KiB, i.e. one full wave of the cell-sponge kernel on 148 SMs (7 CTAs of 128
@@ -661,24 +679,20 @@ extern "C" int cdx_slot_commit_range_host(cdx_ctx* ctx, const uint8_t* data, siz
   return commit_host_range(ctx, data, n_local_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, false, out);
 }
 
-// File-resident slot.  Three overlapped stages: parallel pread into one of two pinned chunks (host threads), H2D of that
-// chunk into the current device tile (copy stream), cell sponge per finished tile (alternating compute streams).
-extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t offset, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
-  if (!ctx || !path || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
-  *out = nullptr;
-  int rc = check_shape(ctx, n_bytes, cell_size, block_size);
-  if (rc) return rc;
-  const int fd = open(path, O_RDONLY);
-  if (fd < 0) return fail(ctx, CDX_ERR_ARG, "cannot open slot data file `%s`", path);
+// Slot bytes that are not directly DMA-able (a file, or pageable host memory -- what a Nim seq[byte] is).  Three
+// overlapped stages: host threads fill one of two pinned chunks through `fill(dst, offset, len)`, H2D of that chunk
+// into the current device tile (copy stream), cell sponge per finished tile (alternating compute streams).
+static int commit_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block, uint64_t n_total_blocks,
+                         int top_level, bool whole_slot, const ChunkFill& fill, cdx_slot** out) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t n_blocks = n_bytes / block_size;
+  if (whole_slot) n_total_blocks = n_blocks;
   const size_t chunk_bytes_target = (size_t)64 << 20;                       // pinned chunk
   size_t chunk_blocks = chunk_bytes_target / block_size ? chunk_bytes_target / block_size : 1;
   size_t tile_blocks = 4 * chunk_blocks;                                    // device tile = 4 chunks = 256 MiB (one sponge wave)
   if (tile_blocks > n_blocks) tile_blocks = n_blocks;
   if (chunk_blocks > tile_blocks) chunk_blocks = tile_blocks;
   const size_t chunk_bytes = chunk_blocks * block_size, tile_bytes = tile_blocks * block_size;
-  auto cleanup_fd = [&]() { close(fd); };
   if (ctx->pinned_bytes < chunk_bytes) {
     for (int i = 0; i < 2; ++i) {
       if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
@@ -686,32 +700,23 @@ extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t off
     }
     ctx->pinned_bytes = 0;
     for (int i = 0; i < 2; ++i)
-      if (cudaHostAlloc(&ctx->h_pinned[i], chunk_bytes, cudaHostAllocDefault) != cudaSuccess) {
-        cleanup_fd();
+      if (cudaHostAlloc(&ctx->h_pinned[i], chunk_bytes, cudaHostAllocDefault) != cudaSuccess)
         return fail(ctx, CDX_ERR_ALLOC, "cudaHostAlloc of %zu bytes failed", chunk_bytes);
-      }
     ctx->pinned_bytes = chunk_bytes;
   }
-  rc = ensure_stage(ctx, tile_bytes);
-  if (rc) { cleanup_fd(); return rc; }
+  int rc = ensure_stage(ctx, tile_bytes);
+  if (rc) return rc;
   cdx_slot* s = nullptr;
-  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, 0, n_blocks, 0, ctx->stream, &s);
-  if (rc) { cleanup_fd(); return rc; }
+  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, first_block, n_total_blocks, top_level, ctx->stream, &s);
+  if (rc) return rc;
   const size_t cpb = block_size / cell_size;
-  auto read_chunk_parallel = [&](uint8_t* dst, uint64_t file_off, size_t len) {
-    const unsigned n_thr = 4;
+  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned n_thr = hw >= 16 ? 8 : (hw >= 8 ? 4 : 2);
+  auto fill_chunk_parallel = [&](uint8_t* dst, uint64_t off, size_t len) {
     std::vector<std::thread> thr;
     for (unsigned t = 0; t < n_thr; ++t) {
       const size_t a = len * t / n_thr, b = len * (t + 1) / n_thr;
-      thr.emplace_back([=]() {
-        size_t pos = a;
-        while (pos < b) {
-          const ssize_t got = pread(fd, dst + pos, b - pos, (off_t)(file_off + pos));
-          if (got <= 0) break;                                              // EOF or error: the rest reads as zeros
-          pos += (size_t)got;
-        }
-        if (pos < b) memset(dst + pos, 0, b - pos);
-      });
+      if (b > a) thr.emplace_back([&fill, dst, off, a, b]() { fill(dst + a, off + a, b - a); });
     }
     for (auto& t : thr) t.join();
   };
@@ -728,7 +733,7 @@ extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t off
         const int pb = (int)(chunk_no & 1);
         const size_t cnb = nb - cb < chunk_blocks ? nb - cb : chunk_blocks;
         if (chunk_no >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_h2d[pb]));                  // pinned chunk pb drained
-        read_chunk_parallel((uint8_t*)ctx->h_pinned[pb], offset + (uint64_t)(done_blocks + cb) * block_size, cnb * block_size);
+        fill_chunk_parallel((uint8_t*)ctx->h_pinned[pb], (uint64_t)(done_blocks + cb) * block_size, cnb * block_size);
         CU_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->d_stage[b] + cb * block_size, ctx->h_pinned[pb], cnb * block_size, cudaMemcpyHostToDevice,
                                     ctx->copy_stream));
         CU_TRY(ctx, cudaEventRecord(ctx->ev_h2d[pb], ctx->copy_stream));
@@ -744,13 +749,14 @@ extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t off
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     int r = build_local_trees(s);
     if (r) return r;
-    r = build_top(s, s->low[0], true);
-    if (r) return r;
+    if (whole_slot) {
+      r = build_top(s, s->low[0], true);
+      if (r) return r;
+    }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CDX_OK;
   };
   rc = body();
-  cleanup_fd();
   if (rc) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream2);
@@ -760,6 +766,27 @@ extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t off
   }
   *out = s;
   return CDX_OK;
+}
+
+extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t offset, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
+  if (!ctx || !path || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  *out = nullptr;
+  int rc = check_shape(ctx, n_bytes, cell_size, block_size);
+  if (rc) return rc;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(ctx, CDX_ERR_ARG, "cannot open slot data file `%s`", path);
+  ChunkFill fill = [fd, offset](uint8_t* dst, uint64_t off, size_t len) {
+    size_t pos = 0;
+    while (pos < len) {
+      const ssize_t got = pread(fd, dst + pos, len - pos, (off_t)(offset + off + pos));
+      if (got <= 0) break;                                                  // EOF or error: the rest reads as zeros (slot.nim:64-65)
+      pos += (size_t)got;
+    }
+    if (pos < len) memset(dst + pos, 0, len - pos);
+  };
+  rc = commit_staged(ctx, n_bytes, cell_size, block_size, 0, 0, 0, true, fill, out);
+  close(fd);
+  return rc;
 }
 
 extern "C" int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells, size_t cell_size, size_t block_size, cdx_slot** out) {
