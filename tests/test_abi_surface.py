@@ -56,3 +56,20 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert not pat.search(text), f"{os.path.join(dp, f)} references the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    """cgo / Nim importc / ctypes-style consumers compile include/codex_commit.h as C: no C++ in the declarations"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include")
+    src = tmp_path / "use.c"
+    src.write_text('#include "codex_commit.h"\n'
+                   "int probe(cdx_ctx* c, cdx_slot* s, unsigned char* out) {\n"
+                   "  unsigned long long idx[1] = {0};\n"
+                   "  if (cdx_slot_root(s, out) != CDX_OK) return 1;\n"
+                   "  return cdx_slot_cell_paths(s, (const uint64_t*)idx, 1, 32, out, 0) + (c == 0);\n"
+                   "}\n")
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        res = subprocess.run([cc, std, "-Wall", "-Werror", "-pedantic", "-x", "c" if cc == "gcc" else "c++", "-I", hdr, "-c", str(src), "-o",
+                              str(tmp_path / "use.o")], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
