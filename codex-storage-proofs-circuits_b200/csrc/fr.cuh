@@ -23,7 +23,7 @@
 //   In particular inputs < 2r give outputs < 2r; inputs < r give outputs < 1.19 r.
 //   add_mod / dbl_mod take inputs < r and return < r.  reduce_once maps [0,2r) -> [0,r).
 //
-// The four carry-chain primitives below are inline PTX.  Compiling this header with a host compiler is only
+// The carry-chain primitives below are inline PTX.  Compiling this header with a host compiler is only
 // possible with -DCDX_HOST_EMUL, which pulls C emulations of exactly those primitives from
 // tests/host_emul/fr_rows_host.h so that the limb-level logic ABOVE them (reductions, Poseidon2 schedule, byte
 // chunking) can be unit-tested without a GPU.  The product library is always compiled by nvcc for sm_100a and
@@ -157,18 +157,85 @@ CDX_D void mont_row_redc_shift(uint32_t* e, uint32_t* o) {
         "n"(CDX_N6));
 }
 
-// Carry-flag building blocks for the squaring's product rows.  Each is one asm statement; the PTX condition code
-// carries from one to the next (compiler-generated PTX never writes CC, and `volatile` keeps the order).
-CDX_D void cc_mad_first(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {   // (hi:lo) += a*b, carry out
-  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+// Product rows of the streaming squaring (mont_sqr): mont_row_next with a multiplicand of NPROD < 8 limbs, i.e. the
+// same window shift, with plain carry propagation where the row has no product.  v = multiplicand limbs, b = multiplier.
+CDX_D void sqr_row7(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t b) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %8, %17, %23, %10;  madc.hi.cc.u32 %9, %17, %23, %11;\n\t"
+      "madc.lo.cc.u32 %10, %19, %23, %12; madc.hi.cc.u32 %11, %19, %23, %13;\n\t"
+      "madc.lo.cc.u32 %12, %21, %23, %14; madc.hi.cc.u32 %13, %21, %23, %15;\n\t"
+      "addc.u32 %14, 0, 0;                mov.u32 %15, 0;\n\t"
+      "mad.lo.cc.u32 %0, %16, %23, %0;  madc.hi.cc.u32 %1, %16, %23, %1;\n\t"
+      "madc.lo.cc.u32 %2, %18, %23, %2; madc.hi.cc.u32 %3, %18, %23, %3;\n\t"
+      "madc.lo.cc.u32 %4, %20, %23, %4; madc.hi.cc.u32 %5, %20, %23, %5;\n\t"
+      "madc.lo.cc.u32 %6, %22, %23, %6; madc.hi.cc.u32 %7, %22, %23, %7;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      "}"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(b));
 }
-CDX_D void cc_mad_next(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {    // carry in and out
-  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+CDX_D void sqr_row6(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t b) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %8, %17, %22, %10;  madc.hi.cc.u32 %9, %17, %22, %11;\n\t"
+      "madc.lo.cc.u32 %10, %19, %22, %12; madc.hi.cc.u32 %11, %19, %22, %13;\n\t"
+      "madc.lo.cc.u32 %12, %21, %22, %14; madc.hi.cc.u32 %13, %21, %22, %15;\n\t"
+      "addc.u32 %14, 0, 0;                mov.u32 %15, 0;\n\t"
+      "mad.lo.cc.u32 %0, %16, %22, %0;  madc.hi.cc.u32 %1, %16, %22, %1;\n\t"
+      "madc.lo.cc.u32 %2, %18, %22, %2; madc.hi.cc.u32 %3, %18, %22, %3;\n\t"
+      "madc.lo.cc.u32 %4, %20, %22, %4; madc.hi.cc.u32 %5, %20, %22, %5;\n\t"
+      "addc.cc.u32 %6, %6, 0;           addc.cc.u32 %7, %7, 0;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      "}"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(b));
 }
-CDX_D void cc_carry_into(uint32_t& x) { asm volatile("addc.u32 %0, %0, 0;" : "+r"(x)); }                 // x += carry
-CDX_D void cc_add_first(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
-CDX_D void cc_add_next(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
-CDX_D void cc_add_last(uint32_t& r, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+CDX_D void sqr_row5(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t b) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %8, %17, %21, %10;  madc.hi.cc.u32 %9, %17, %21, %11;\n\t"
+      "madc.lo.cc.u32 %10, %19, %21, %12; madc.hi.cc.u32 %11, %19, %21, %13;\n\t"
+      "addc.cc.u32 %12, %14, 0;           addc.cc.u32 %13, %15, 0;\n\t"
+      "addc.u32 %14, 0, 0;                mov.u32 %15, 0;\n\t"
+      "mad.lo.cc.u32 %0, %16, %21, %0;  madc.hi.cc.u32 %1, %16, %21, %1;\n\t"
+      "madc.lo.cc.u32 %2, %18, %21, %2; madc.hi.cc.u32 %3, %18, %21, %3;\n\t"
+      "madc.lo.cc.u32 %4, %20, %21, %4; madc.hi.cc.u32 %5, %20, %21, %5;\n\t"
+      "addc.cc.u32 %6, %6, 0;           addc.cc.u32 %7, %7, 0;\n\t"
+      "addc.u32 %15, %15, 0;\n\t"
+      "}"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(b));
+}
+// The ten operand products that lie entirely in the upper half of the square (rows a4..a7), added to the final
+// window: e pairs sit at result positions (0,1),(2,3),(4,5),(6,7), o[2..7] at (1,2),(3,4),(5,6) -- o ends one limb below
+// the top of the result, so a carry out of o[7] goes into e[7].
+// in: a4 a5 a6 a7 = %14..%17, s5 s6 s7 (a_j << 1) = %18..%20, d6 d7 (doubled limbs) = %21 %22
+CDX_D void sqr_upper(uint32_t* e, uint32_t* o, const uint32_t* a, const uint32_t* sh, const uint32_t* d) {
+  asm("{\n\t"
+      "mad.lo.cc.u32 %8, %18, %14, %8;    madc.hi.cc.u32 %9, %18, %14, %9;\n\t"
+      "madc.lo.cc.u32 %10, %22, %14, %10; madc.hi.cc.u32 %11, %22, %14, %11;\n\t"
+      "madc.lo.cc.u32 %12, %20, %16, %12; madc.hi.cc.u32 %13, %20, %16, %13;\n\t"
+      "addc.u32 %7, %7, 0;\n\t"
+      "mad.lo.cc.u32 %10, %19, %15, %10;  madc.hi.cc.u32 %11, %19, %15, %11;\n\t"
+      "addc.cc.u32 %12, %12, 0;           addc.cc.u32 %13, %13, 0;\n\t"
+      "addc.u32 %7, %7, 0;\n\t"
+      "mad.lo.cc.u32 %0, %14, %14, %0;  madc.hi.cc.u32 %1, %14, %14, %1;\n\t"
+      "madc.lo.cc.u32 %2, %21, %14, %2; madc.hi.cc.u32 %3, %21, %14, %3;\n\t"
+      "madc.lo.cc.u32 %4, %22, %15, %4; madc.hi.cc.u32 %5, %22, %15, %5;\n\t"
+      "madc.lo.cc.u32 %6, %17, %17, %6; madc.hi.u32 %7, %17, %17, %7;\n\t"
+      "mad.lo.cc.u32 %2, %15, %15, %2;  madc.hi.cc.u32 %3, %15, %15, %3;\n\t"
+      "madc.lo.cc.u32 %4, %16, %16, %4; madc.hi.cc.u32 %5, %16, %16, %5;\n\t"
+      "addc.cc.u32 %6, %6, 0;           addc.u32 %7, %7, 0;\n\t"
+      "}"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(sh[5]), "r"(sh[6]), "r"(sh[7]), "r"(d[6]), "r"(d[7]));
+}
+
 CDX_D uint32_t shl1_funnel(uint32_t lo, uint32_t hi) { return __funnelshift_l(lo, hi, 1); }              // (hi:lo << 1) >> 32
 
 // r = e + (o >> 32 limbs aligned as after a row): r[k] = e[k] + o[k+1] with carry
@@ -189,21 +256,18 @@ CDX_D void add256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
 }
 
-// d = a - r (the modulus); returns 1 if that borrowed (a < r), else 0
-CDX_D uint32_t sub_modulus(uint32_t* d, const uint32_t* a) {
-  uint32_t borrow;
-  asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20;"
-      "subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22; subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24;"
-      "subc.u32 %8, 0, 0;"
-      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
-        "=r"(borrow)
+// d = a - r (the modulus) mod 2^256.  For a < 2r the sign bit of d tells whether that borrowed: a < r gives
+// d > 2^256 - r > 2^255, a >= r gives d < r < 2^254 -- so the caller needs neither the borrow flag nor a compare chain.
+CDX_D void sub_modulus(uint32_t* d, const uint32_t* a) {
+  asm("sub.cc.u32 %0, %8, %16; subc.cc.u32 %1, %9, %17; subc.cc.u32 %2, %10, %18; subc.cc.u32 %3, %11, %19;"
+      "subc.cc.u32 %4, %12, %20; subc.cc.u32 %5, %13, %21; subc.cc.u32 %6, %14, %22; subc.u32 %7, %15, %23;"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "n"(CDX_N0),
         "n"(CDX_N1), "n"(CDX_N2), "n"(CDX_N3), "n"(CDX_N4), "n"(CDX_N5), "n"(CDX_N6), "n"(CDX_N7));
-  return borrow & 1u;
 }
 #elif defined(CDX_HOST_EMUL)
 }  // namespace cdx
-#include "fr_rows_host.h"  // tests/host_emul: C emulation of the six primitives above (unit tests only)
+#include "fr_rows_host.h"  // tests/host_emul: C emulation of the primitives above (unit tests only)
 namespace cdx {
 #else
 #if !defined(__CUDACC__)
@@ -214,16 +278,14 @@ void mont_row_first(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
 void mont_row_next(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
 void mont_row_redc(uint32_t*, uint32_t*);
 void mont_row_redc_shift(uint32_t*, uint32_t*);
-void cc_mad_first(uint32_t&, uint32_t&, uint32_t, uint32_t);
-void cc_mad_next(uint32_t&, uint32_t&, uint32_t, uint32_t);
-void cc_carry_into(uint32_t&);
-void cc_add_first(uint32_t&, uint32_t, uint32_t);
-void cc_add_next(uint32_t&, uint32_t, uint32_t);
-void cc_add_last(uint32_t&, uint32_t, uint32_t);
+void sqr_row7(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
+void sqr_row6(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
+void sqr_row5(uint32_t*, uint32_t*, const uint32_t*, uint32_t);
+void sqr_upper(uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*);
 uint32_t shl1_funnel(uint32_t, uint32_t);
 void mont_merge(uint32_t*, const uint32_t*, const uint32_t*);
 void add256(uint32_t*, const uint32_t*, const uint32_t*);
-uint32_t sub_modulus(uint32_t*, const uint32_t*);
+void sub_modulus(uint32_t*, const uint32_t*);
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
@@ -249,84 +311,48 @@ CDX_D Fr mont_mul(const Fr& a, const Fr& b) {
 }
 
 // a*a*2^-256 mod r with 36 instead of 64 operand products (2/3 of all multiplications on this path are squarings:
-// x^2 and x^4 of every S-box).  a < 2r; result < a^2/2^256 + r < 2r, same contract as mont_mul.
-//   1. cross products a_i*a_j (i < j), 28 of them, row by row into an even- and an odd-aligned 512-bit accumulator
-//      (a chain never has to ripple: the limb above its last pair has only ever received carries);
-//   2. T = 2*(E + O) + sum a_i^2 * 2^(64 i): one add chain, one funnel-shift pass, one 8-product carry chain;
-//   3. Montgomery-reduce the low half with 8 reduction-only rows, add the high half (< 0.76 r, no overflow).
+// x^2 and x^4 of every S-box), in the same row pipeline as mont_mul.  a < 2r (so a < 2^255); result < a^2/2^256 + r < 2r.
+//   a^2 = sum_i a_i * V_i * 2^(64 i),  V_i = a_i + 2^32 * 2*floor(a / 2^(32(i+1)))   (8-i limbs: a_i, a_{i+1} << 1, then
+//   the limbs of 2a), so product row i starts at limb 2i and the window can drop two limbs (two reduction rows) per
+//   product row.  Rows 4..7 lie entirely above the eight reduced limbs and are added to the final window.
+// Window bound: after two reduction rows the window is < r + small, a product row adds < 2a, so it stays < 2^256
+// as long as 2a + r < 2^256, i.e. a < 2.14 r.
 CDX_D Fr mont_sqr(const Fr& a) {
-  uint32_t E[16], O[16];
+  uint32_t d[8], sh[8];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) E[k] = O[k] = 0;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    {  // products landing on even positions i+j
-      bool first = true;
-      int last = -1;
-#pragma unroll
-      for (int j = i + 1; j < 8; ++j) {
-        if (((i + j) & 1) == 0) {
-          if (first) cc_mad_first(E[i + j], E[i + j + 1], a.l[i], a.l[j]);
-          else cc_mad_next(E[i + j], E[i + j + 1], a.l[i], a.l[j]);
-          first = false;
-          last = i + j;
-        }
-      }
-      if (!first) cc_carry_into(E[last + 2]);
-    }
-    {  // products landing on odd positions
-      bool first = true;
-      int last = -1;
-#pragma unroll
-      for (int j = i + 1; j < 8; ++j) {
-        if (((i + j) & 1) == 1) {
-          if (first) cc_mad_first(O[i + j], O[i + j + 1], a.l[i], a.l[j]);
-          else cc_mad_next(O[i + j], O[i + j + 1], a.l[i], a.l[j]);
-          first = false;
-          last = i + j;
-        }
-      }
-      if (!first) cc_carry_into(O[last + 2]);
-    }
+  for (int j = 1; j < 8; ++j) {
+    d[j] = shl1_funnel(a.l[j - 1], a.l[j]);     // limb j of 2a
+    sh[j] = a.l[j] << 1;                        // limb j of 2*(a with the limbs below j cleared)
   }
-  // S = E + O (positions 1..15), then T = 2S
-  uint32_t S[16], T[16];
-  S[0] = 0;
-  cc_add_first(S[1], E[1], O[1]);
-#pragma unroll
-  for (int k = 2; k < 15; ++k) cc_add_next(S[k], E[k], O[k]);
-  cc_add_last(S[15], E[15], O[15]);
-  T[0] = 0;
-#pragma unroll
-  for (int k = 1; k < 16; ++k) T[k] = shl1_funnel(S[k - 1], S[k]);
-  // + diagonal squares, one carry chain over all 16 limbs
-  cc_mad_first(T[0], T[1], a.l[0], a.l[0]);
-#pragma unroll
-  for (int i = 1; i < 8; ++i) cc_mad_next(T[2 * i], T[2 * i + 1], a.l[i], a.l[i]);
-  // reduce the low half
+  d[0] = sh[0] = 0;
+  const uint32_t v0[8] = {a.l[0], sh[1], d[2], d[3], d[4], d[5], d[6], d[7]};
+  const uint32_t v1[7] = {a.l[1], sh[2], d[3], d[4], d[5], d[6], d[7]};
+  const uint32_t v2[6] = {a.l[2], sh[3], d[4], d[5], d[6], d[7]};
+  const uint32_t v3[5] = {a.l[3], sh[4], d[5], d[6], d[7]};
   uint32_t e[8], o[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    e[k] = T[k];
-    o[k] = 0;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    mont_row_redc_shift(e, o);
-    mont_row_redc_shift(o, e);
-  }
-  Fr u, hi, r;
-  mont_merge(u.l, e, o);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) hi.l[k] = T[8 + k];
-  add256(r.l, u.l, hi.l);
+  mont_row_first(e, o, v0, a.l[0]);
+  mont_row_redc(e, o);
+  mont_row_redc_shift(o, e);
+  sqr_row7(e, o, v1, a.l[1]);
+  mont_row_redc(e, o);
+  mont_row_redc_shift(o, e);
+  sqr_row6(e, o, v2, a.l[2]);
+  mont_row_redc(e, o);
+  mont_row_redc_shift(o, e);
+  sqr_row5(e, o, v3, a.l[3]);
+  mont_row_redc(e, o);
+  mont_row_redc_shift(o, e);
+  sqr_upper(e, o, a.l, sh, d);
+  Fr r;
+  mont_merge(r.l, e, o);
   return r;
 }
 
 // [0, 2r) -> [0, r)
 CDX_D Fr reduce_once(const Fr& a) {
   Fr d;
-  uint32_t lt = sub_modulus(d.l, a.l);
+  sub_modulus(d.l, a.l);
+  const bool lt = (int32_t)d.l[7] < 0;   // a < r (see sub_modulus)
   Fr r;
 #pragma unroll
   for (int i = 0; i < 8; ++i) r.l[i] = lt ? a.l[i] : d.l[i];

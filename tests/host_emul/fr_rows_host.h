@@ -1,4 +1,4 @@
-// fr_rows_host.h -- UNIT-TEST ONLY.  Plain C++ emulation of the six inline-PTX carry-chain primitives of
+// fr_rows_host.h -- UNIT-TEST ONLY.  Plain C++ emulation of the inline-PTX carry-chain primitives of
 // codex-storage-proofs-circuits_b200/csrc/fr.cuh, instruction by instruction (an explicit carry flag stands in
 // for the PTX condition code), so the limb-level logic layered on top of them can be exercised by g++ on a
 // machine without a GPU (tests/test_limb_logic_host.py).  Never compiled into the product library.
@@ -75,18 +75,52 @@ inline void mont_row_redc_shift(uint32_t* e, uint32_t* o) {
   o[7] = c.addc(o[7], 0);
 }
 
-// statement-level primitives: the PTX condition code lives across asm statements; here it is a thread-local flag
-static thread_local emul::CC g_cc;
-inline void cc_mad_first(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = g_cc.mad_lo_cc(a, b, lo); hi = g_cc.madc_hi_cc(a, b, hi); }
-inline void cc_mad_next(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = g_cc.madc_lo_cc(a, b, lo); hi = g_cc.madc_hi_cc(a, b, hi); }
-inline void cc_carry_into(uint32_t& x) {
-  const uint64_t s = (uint64_t)x + g_cc.cf;
-  if (s >> 32) __builtin_trap();   // a chain end must never overflow its carry limb (the device code cannot see this)
-  x = (uint32_t)s;
+template <int NPROD>
+inline void sqr_row_emul(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t b) {
+  emul::CC c;
+  e[0] = c.add_cc(e[0], o[1]);
+  for (int j = 0; j < 3; ++j) {
+    const int k = 2 * j + 1;
+    if (k < NPROD) { o[2 * j] = c.madc_lo_cc(v[k], b, o[2 * j + 2]); o[2 * j + 1] = c.madc_hi_cc(v[k], b, o[2 * j + 3]); }
+    else { o[2 * j] = c.addc_cc(o[2 * j + 2], 0); o[2 * j + 1] = c.addc_cc(o[2 * j + 3], 0); }
+  }
+  o[6] = c.addc(0, 0); o[7] = 0;                    // k = 7 is never present (NPROD <= 7)
+  c.cf = 0;
+  for (int j = 0; j < 4; ++j) {
+    const int k = 2 * j;
+    if (k < NPROD) {
+      e[2 * j] = j == 0 ? c.mad_lo_cc(v[k], b, e[0]) : c.madc_lo_cc(v[k], b, e[2 * j]);
+      e[2 * j + 1] = c.madc_hi_cc(v[k], b, e[2 * j + 1]);
+    } else { e[2 * j] = c.addc_cc(e[2 * j], 0); e[2 * j + 1] = c.addc_cc(e[2 * j + 1], 0); }
+  }
+  o[7] = c.addc(o[7], 0);
 }
-inline void cc_add_first(uint32_t& r, uint32_t a, uint32_t b) { r = g_cc.add_cc(a, b); }
-inline void cc_add_next(uint32_t& r, uint32_t a, uint32_t b) { r = g_cc.addc_cc(a, b); }
-inline void cc_add_last(uint32_t& r, uint32_t a, uint32_t b) { r = g_cc.addc(a, b); }
+inline void sqr_row7(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t b) { sqr_row_emul<7>(e, o, v, b); }
+inline void sqr_row6(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t b) { sqr_row_emul<6>(e, o, v, b); }
+inline void sqr_row5(uint32_t* e, uint32_t* o, const uint32_t* v, uint32_t b) { sqr_row_emul<5>(e, o, v, b); }
+
+inline void sqr_upper(uint32_t* e, uint32_t* o, const uint32_t* a, const uint32_t* sh, const uint32_t* d) {
+  emul::CC c;
+  o[2] = c.mad_lo_cc(sh[5], a[4], o[2]); o[3] = c.madc_hi_cc(sh[5], a[4], o[3]);
+  o[4] = c.madc_lo_cc(d[7], a[4], o[4]); o[5] = c.madc_hi_cc(d[7], a[4], o[5]);
+  o[6] = c.madc_lo_cc(sh[7], a[6], o[6]); o[7] = c.madc_hi_cc(sh[7], a[6], o[7]);
+  e[7] = c.addc_cc(e[7], 0);
+  if (c.cf) __builtin_trap();            // the result fits 256 bits: nothing may carry out of e[7]
+  o[4] = c.mad_lo_cc(sh[6], a[5], o[4]); o[5] = c.madc_hi_cc(sh[6], a[5], o[5]);
+  o[6] = c.addc_cc(o[6], 0);             o[7] = c.addc_cc(o[7], 0);
+  e[7] = c.addc_cc(e[7], 0);
+  if (c.cf) __builtin_trap();
+  e[0] = c.mad_lo_cc(a[4], a[4], e[0]);  e[1] = c.madc_hi_cc(a[4], a[4], e[1]);
+  e[2] = c.madc_lo_cc(d[6], a[4], e[2]); e[3] = c.madc_hi_cc(d[6], a[4], e[3]);
+  e[4] = c.madc_lo_cc(d[7], a[5], e[4]); e[5] = c.madc_hi_cc(d[7], a[5], e[5]);
+  e[6] = c.madc_lo_cc(a[7], a[7], e[6]); e[7] = c.madc_hi_cc(a[7], a[7], e[7]);
+  if (c.cf) __builtin_trap();
+  e[2] = c.mad_lo_cc(a[5], a[5], e[2]);  e[3] = c.madc_hi_cc(a[5], a[5], e[3]);
+  e[4] = c.madc_lo_cc(a[6], a[6], e[4]); e[5] = c.madc_hi_cc(a[6], a[6], e[5]);
+  e[6] = c.addc_cc(e[6], 0);             e[7] = c.addc_cc(e[7], 0);
+  if (c.cf) __builtin_trap();
+}
+
 inline uint32_t shl1_funnel(uint32_t lo, uint32_t hi) { return (hi << 1) | (lo >> 31); }
 
 inline void mont_merge(uint32_t* r, const uint32_t* e, const uint32_t* o) {
@@ -103,10 +137,10 @@ inline void add256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   r[7] = c.addc(a[7], b[7]);
 }
 
-inline uint32_t sub_modulus(uint32_t* d, const uint32_t* a) {
+inline void sub_modulus(uint32_t* d, const uint32_t* a) {
   emul::CC c;
   d[0] = c.sub_cc(a[0], kModHost[0]);
   for (int k = 1; k < 8; ++k) d[k] = c.subc_cc(a[k], kModHost[k]);
-  return c.cf & 1u;
+  if ((c.cf & 1u) != (d[7] >> 31)) __builtin_trap();   // the caller reads the borrow off the sign bit: only valid for a < 2r
 }
 }  // namespace cdx
