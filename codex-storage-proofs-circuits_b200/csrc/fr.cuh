@@ -138,22 +138,25 @@ CDX_D void mont_row_redc(uint32_t* e, uint32_t* o) {
 // (positions 0..7), o the previous window after its divide by 2^32 (o[k] at position k-1, o[0] dead).  On exit o is
 // the new odd-aligned accumulator (positions 1..8) and e the even one with its low limb cancelled.
 CDX_D void mont_row_redc_shift(uint32_t* e, uint32_t* o) {
-  const uint32_t m = (e[0] + o[1]) * CDX_NP;          // from the true low limb of the window
+  // the Montgomery factor comes from the true low limb of the window, e[0] + o[1]: formed once, by the add that also
+  // starts the carry chain (mul.lo does not touch the condition code)
   asm("{\n\t"
+      ".reg .u32 m;\n\t"
       "add.cc.u32 %0, %0, %9;\n\t"
-      "madc.lo.cc.u32 %8, %17, %16, %10;  madc.hi.cc.u32 %9, %17, %16, %11;\n\t"
-      "madc.lo.cc.u32 %10, %19, %16, %12; madc.hi.cc.u32 %11, %19, %16, %13;\n\t"
-      "madc.lo.cc.u32 %12, %21, %16, %14; madc.hi.cc.u32 %13, %21, %16, %15;\n\t"
-      "madc.lo.cc.u32 %14, %23, %16, 0;   madc.hi.u32 %15, %23, %16, 0;\n\t"
-      "mad.lo.cc.u32 %0, %18, %16, %0;  madc.hi.cc.u32 %1, %18, %16, %1;\n\t"
-      "madc.lo.cc.u32 %2, %20, %16, %2; madc.hi.cc.u32 %3, %20, %16, %3;\n\t"
-      "madc.lo.cc.u32 %4, %22, %16, %4; madc.hi.cc.u32 %5, %22, %16, %5;\n\t"
-      "madc.lo.cc.u32 %6, %24, %16, %6; madc.hi.cc.u32 %7, %24, %16, %7;\n\t"
+      "mul.lo.u32 m, %0, %16;\n\t"
+      "madc.lo.cc.u32 %8, %17, m, %10;  madc.hi.cc.u32 %9, %17, m, %11;\n\t"
+      "madc.lo.cc.u32 %10, %19, m, %12; madc.hi.cc.u32 %11, %19, m, %13;\n\t"
+      "madc.lo.cc.u32 %12, %21, m, %14; madc.hi.cc.u32 %13, %21, m, %15;\n\t"
+      "madc.lo.cc.u32 %14, %23, m, 0;   madc.hi.u32 %15, %23, m, 0;\n\t"
+      "mad.lo.cc.u32 %0, %18, m, %0;  madc.hi.cc.u32 %1, %18, m, %1;\n\t"
+      "madc.lo.cc.u32 %2, %20, m, %2; madc.hi.cc.u32 %3, %20, m, %3;\n\t"
+      "madc.lo.cc.u32 %4, %22, m, %4; madc.hi.cc.u32 %5, %22, m, %5;\n\t"
+      "madc.lo.cc.u32 %6, %24, m, %6; madc.hi.cc.u32 %7, %24, m, %7;\n\t"
       "addc.u32 %15, %15, 0;\n\t"
       "}"
       : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
         "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
-      : "r"(m), "n"(CDX_N1), "n"(CDX_N0), "n"(CDX_N3), "n"(CDX_N2), "n"(CDX_N5), "n"(CDX_N4), "n"(CDX_N7),
+      : "n"(CDX_NP), "n"(CDX_N1), "n"(CDX_N0), "n"(CDX_N3), "n"(CDX_N2), "n"(CDX_N5), "n"(CDX_N4), "n"(CDX_N7),
         "n"(CDX_N6));
 }
 
@@ -322,7 +325,7 @@ CDX_D Fr mont_sqr(const Fr& a) {
 #pragma unroll
   for (int j = 1; j < 8; ++j) {
     d[j] = shl1_funnel(a.l[j - 1], a.l[j]);     // limb j of 2a
-    sh[j] = a.l[j] << 1;                        // limb j of 2*(a with the limbs below j cleared)
+    sh[j] = shl1_funnel(0u, a.l[j]);            // a_j << 1 = limb j of 2*(a with the limbs below j cleared)
   }
   d[0] = sh[0] = 0;
   const uint32_t v0[8] = {a.l[0], sh[1], d[2], d[3], d[4], d[5], d[6], d[7]};
