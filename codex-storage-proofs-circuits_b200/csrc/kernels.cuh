@@ -25,7 +25,9 @@ static __device__ __forceinline__ void st_felt(uint8_t* p, const Fr& v) {
   q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
+#ifndef CDX_BLOCK
 #define CDX_BLOCK 128
+#endif
 
 // K1: n independent permutations (BASELINE config 2).           Permutation.hs:40-45
 __global__ void __launch_bounds__(CDX_BLOCK) k_permutation_batch(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
@@ -67,7 +69,14 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_hash_cells(const uint32_t* __rest
 // Lane l only ever reads row l, and a box is overwritten only after the step that last read it, so there is no
 // cross-thread hand-shake beyond the warp being convergent.
 //   HBM traffic: each 32-byte sector of the slot is fetched exactly once.
+#ifndef CDX_RING_SLOTS
 #define CDX_RING_SLOTS 6
+#endif
+// resident CTAs per SM the cell kernel is compiled for: 8 x 128 threads caps it at 64 registers (measured 0.8 % faster than
+// the 68 registers ptxas takes when left alone, at 7 CTAs per SM)
+#ifndef CDX_TMA_MIN_CTAS
+#define CDX_TMA_MIN_CTAS 8
+#endif
 #define CDX_SEG_BYTES 32u
 #define CDX_BOX_BYTES (32u * CDX_SEG_BYTES)
 
@@ -138,7 +147,7 @@ struct alignas(64) TensorMap2D {   // layout-compatible with CUtensorMap (128 op
 };
 
 // cell_bytes % 32 == 0; dynamic shared memory: 128 B slack + warps x (CDX_RING_SLOTS x 1 KiB) + barriers
-__global__ void __launch_bounds__(CDX_BLOCK) k_hash_cells_tma(const __grid_constant__ TensorMap2D tmap, size_t n_cells, uint32_t cell_bytes,
+__global__ void __launch_bounds__(CDX_BLOCK, CDX_TMA_MIN_CTAS) k_hash_cells_tma(const __grid_constant__ TensorMap2D tmap, size_t n_cells, uint32_t cell_bytes,
                                                               uint8_t* __restrict__ out) {
   extern __shared__ uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
