@@ -56,6 +56,13 @@ def test_mont_sqr_dedicated(emul):
         assert v <= (a * a >> 256) + R and v < 2 * R
         emul.emul_mont_mul_raw(f2b(a), f2b(a), out2)
         assert b2f(out2.raw) == v
+    # the window bound of the streaming squaring is 2a + r < 2^256, i.e. a < 2.14 r: the emulation traps on any carry out
+    # of the window, so running right up to that bound checks the bound itself (the S-box never goes beyond 2r)
+    limit = ((1 << 256) - R) // 2
+    for a in [limit - 1, limit - (1 << 200), 2 * R, 2 * R + 12345] + [rnd.randrange(2 * R, limit) for _ in range(500)]:
+        emul.emul_mont_sqr_raw(f2b(a), out)
+        v = b2f(out.raw)
+        assert v % R == a * a * rinv % R and v <= (a * a >> 256) + R
 
 
 def test_permutation_and_compress(emul, orc):
