@@ -98,6 +98,23 @@ def test_one_gib_slot_properties(ctx, orc, torch_mod):
     host_all = d.cpu().numpy()
     with ctx.slot_commit_host(host_all) as slot2:
         assert slot2.root == root
+    # the same bytes from pinned memory (direct async copies instead of the pinned-chunk pipeline pageable memory takes)
+    pinned = torch.empty(n_blocks * 65536, dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(d)
+    torch.cuda.synchronize()
+    with ctx.slot_commit_host(pinned.data_ptr(), n_bytes=n_blocks * 65536) as slot3:
+        assert slot3.root == root
+    # two ranks' worth of pageable host ranges (512 MiB each: the chunk pipeline with a non-zero first block), exchanged
+    sharded = importlib.import_module(PKG + ".sharded")
+    half = n_blocks // 2
+    shards = [sharded.GpuShard(ctx.slot_commit_range_host(host_all[k * half * 65536:(k + 1) * half * 65536], 2048, 65536, k * half, n_blocks, 13))
+              for k in range(2)]
+    gathered = torch.cat([s.subtree_roots_tensor() for s in shards]).contiguous()
+    for s in shards:
+        s.set_top_tensor(gathered)
+    assert [s.root for s in shards] == [root, root]
+    for s in shards:
+        s.free()
 
 
 def test_idempotence_and_sensitivity(ctx, torch_mod):
