@@ -634,10 +634,16 @@ static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
     CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));              // the slot's buffers were allocated on stream
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
     size_t done = 0;
+    const size_t first_tile = tile_blocks / 8 ? tile_blocks / 8 : 1;
+    const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
     for (int t = 0; done < n_blocks; ++t) {
       const int b = t & 1;
       cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
-      const size_t nb = n_blocks - done < tile_blocks ? n_blocks - done : tile_blocks;
+      // the copy of tile 0 is the only one nothing overlaps: keep it short (1/8 tile), then realign with tile 1
+      size_t want = tile_blocks;
+      if (ramp && t == 0) want = first_tile;
+      else if (ramp && t == 1) want = tile_blocks - first_tile;
+      const size_t nb = n_blocks - done < want ? n_blocks - done : want;
       if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
       CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, ctx->copy_stream));
       CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
@@ -724,10 +730,15 @@ static int commit_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t 
     CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
     size_t done_blocks = 0, chunk_no = 0;
+    const bool ramp = n_blocks > tile_blocks && tile_blocks > chunk_blocks;
     for (int t = 0; done_blocks < n_blocks; ++t) {
       const int b = t & 1;
       cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
-      const size_t nb = n_blocks - done_blocks < tile_blocks ? n_blocks - done_blocks : tile_blocks;
+      // tile 0 is one chunk, tile 1 the other three: the sponge starts after one chunk has been filled and copied, not four
+      size_t want = tile_blocks;
+      if (ramp && t == 0) want = chunk_blocks;
+      else if (ramp && t == 1) want = tile_blocks - chunk_blocks;
+      const size_t nb = n_blocks - done_blocks < want ? n_blocks - done_blocks : want;
       if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));   // device tile b free again
       for (size_t cb = 0; cb < nb; cb += chunk_blocks, ++chunk_no) {
         const int pb = (int)(chunk_no & 1);
