@@ -1,11 +1,17 @@
 #!/usr/bin/env python3
 """Compile csrc/capi.cu to a cubin and print, for every S-box loop of a kernel, the FMA-heavy slots H (a 32x32->64
 product counts 2) and the other instructions A -- the two terms of the cost model in DESIGN.md section 4.
-usage: sass_stats.py [kernel-name-substring = k_hash_cells_tma] [extra nvcc flags...]"""
+usage: sass_stats.py [--max-wide N] [kernel-name-substring = k_hash_cells_tma] [extra nvcc flags...]"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-kern = sys.argv[1] if len(sys.argv) > 1 else "k_hash_cells_tma"
-extra = sys.argv[2:]
+args = sys.argv[1:]
+max_wide = 400
+if "--max-wide" in args:                      # also report bodies holding several S-boxes (the external-round body has three)
+    i = args.index("--max-wide")
+    max_wide = int(args[i + 1])
+    del args[i:i + 2]
+kern = args[0] if args else "k_hash_cells_tma"
+extra = args[1:]
 out = os.path.join(ROOT, "gpurun_out", "scratch")
 os.makedirs(out, exist_ok=True)
 cubin = os.path.join(out, "capi.cubin")
@@ -38,7 +44,7 @@ for name, ins in funcs.items():
                 p = t.split()
                 c[p[1] if p[0].startswith("@") else p[0]] += 1
         wide = sum(v for k, v in c.items() if k.startswith("IMAD.WIDE") or k.startswith("IMAD.HI") or k.startswith("UIMAD.WIDE"))
-        if wide < 200 or wide > 400:
+        if wide < 200 or wide > max_wide:
             continue
         other_fma = sum(v for k, v in c.items() if k.startswith("IMAD") and not (k.startswith("IMAD.WIDE") or k.startswith("IMAD.HI")))
         total = sum(c.values())
