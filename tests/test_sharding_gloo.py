@@ -147,3 +147,22 @@ def test_range_planning_properties(pkg):
     t, ranges = sharded.fixed_ranges(163840, 8)                    # bench.py weak-scaling layout
     assert t == 15 and ranges[3] == (3 * 163840, 163840)
     assert sharded.level_width(163840, 15) == 5 and sharded.level_width(5, 3) == 1
+
+
+def test_dataset_planning_helpers(pkg):
+    """host logic of the dataset path (BASELINE config 5): slot sizes, per-slot seeds, LPT packing -- no GPU"""
+    import importlib
+    dataset = importlib.import_module(pkg.__name__ + ".dataset")
+    blocks = dataset.draw_slot_blocks(256, 1 << 30, 100 << 30, seed=12345, pow2_slot=3, pow2_blocks=1 << 17)
+    assert len(blocks) == 256 and blocks[3] == 1 << 17
+    assert all((1 << 30) // 65536 - 1 <= b <= (100 << 30) // 65536 for k, b in enumerate(blocks) if k != 3)
+    assert blocks == dataset.draw_slot_blocks(256, 1 << 30, 100 << 30, seed=12345, pow2_slot=3, pow2_blocks=1 << 17)   # deterministic
+    assert blocks != dataset.draw_slot_blocks(256, 1 << 30, 100 << 30, seed=12346, pow2_slot=3, pow2_blocks=1 << 17)
+    # the reference's per-slot seed rule (dataset.nim:32)
+    assert dataset.slot_seed(12345, 3) == 12345 + 72 + 3003
+    for world in (1, 2, 4, 8):
+        bins = dataset.lpt_assign(blocks, world)
+        assert sorted(k for b in bins for k in b) == list(range(256))          # every slot exactly once
+        loads = [sum(blocks[k] for k in b) for b in bins]
+        assert max(loads) <= 1.02 * sum(blocks) / world                        # LPT on 256 items: within 2 % of even
+    assert dataset.lpt_assign([5], 4) == [[0], [], [], []]
