@@ -8,6 +8,8 @@
 #include <fcntl.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <cerrno>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +41,7 @@ struct cdx_ctx {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
   uint64_t launches = 0;
   bool no_bounce = false;              // CODEX_COMMIT_NO_BOUNCE=1: pageable host slots straight through cudaMemcpyAsync (A/B only)
+  bool tma_smem_set = false;
   bool plain_loads = false;            // CODEX_COMMIT_PLAIN_LOADS=1: per-thread global loads instead of the TMA-staged rows (A/B only)
   char err[256] = {0};
 };
@@ -203,22 +206,39 @@ static encode_tiled_fn get_encode_tiled() {
 
 static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, size_t cell_size, uint8_t* d_out, cudaStream_t st) {
   encode_tiled_fn encode = ctx->plain_loads ? nullptr : get_encode_tiled();
-  if (encode && cell_size % CDX_SEG_BYTES == 0 && cell_size >= 64 && cell_size < (1u << 31) && (uintptr_t)d_data % 16 == 0 && n_cells < (1ull << 32)) {
-    TensorMap2D tmap;
-    const unsigned long long dims[2] = {(unsigned long long)cell_size, (unsigned long long)n_cells};   // innermost first
-    const unsigned long long strides[1] = {(unsigned long long)cell_size};                             // bytes between rows
-    const unsigned box[2] = {CDX_SEG_BYTES, 32u};
-    const unsigned estr[2] = {1u, 1u};
-    // CU_TENSOR_MAP_DATA_TYPE_UINT8 = 0, INTERLEAVE_NONE = 0, SWIZZLE_NONE = 0, L2_PROMOTION_NONE = 0, FLOAT_OOB_FILL_NONE = 0 (zeros)
-    const int rc = encode(&tmap, 0, 2, const_cast<void*>(d_data), dims, strides, box, estr, 0, 0, 0, 0);
-    if (rc != 0) return fail(ctx, CDX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", rc);
+  if (encode && cell_size % CDX_SEG_BYTES == 0 && cell_size >= 64 && cell_size < (1u << 31) && (uintptr_t)d_data % 16 == 0) {
+    // tensor coordinates are signed 32-bit (a row index >= 2^31 would read as out of bounds, i.e. as zeros): launches of at
+    // most 2^30 cells, each with its own tensor-map base
+    const size_t max_cells = (size_t)1 << 30;
     const size_t smem = 128 + (CDX_BLOCK / 32) * (CDX_RING_SLOTS * CDX_BOX_BYTES + 8 * CDX_RING_SLOTS);
-    k_hash_cells_tma<<<grid_for(n_cells), CDX_BLOCK, smem, st>>>(tmap, n_cells, (uint32_t)cell_size, d_out);
-  } else {
-    k_hash_cells<<<grid_for(n_cells), CDX_BLOCK, 0, st>>>((const uint32_t*)d_data, n_cells, (uint32_t)(cell_size / 4), d_out);
+    if (smem > 48 * 1024 && !ctx->tma_smem_set) {   // per device, once: rings of CTAs wider than 7 warps exceed the default 48 KB
+      CU_TRY(ctx, cudaFuncSetAttribute(k_hash_cells_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ctx->tma_smem_set = true;
+    }
+    for (size_t c0 = 0; c0 < n_cells; c0 += max_cells) {
+      const size_t nc = n_cells - c0 < max_cells ? n_cells - c0 : max_cells;
+      TensorMap2D tmap;
+      const unsigned long long dims[2] = {(unsigned long long)cell_size, (unsigned long long)nc};        // innermost first
+      const unsigned long long strides[1] = {(unsigned long long)cell_size};                             // bytes between rows
+      const unsigned box[2] = {CDX_SEG_BYTES, 32u};
+      const unsigned estr[2] = {1u, 1u};
+      // CU_TENSOR_MAP_DATA_TYPE_UINT8 = 0, INTERLEAVE_NONE = 0, SWIZZLE_NONE = 0, L2_PROMOTION_NONE = 0, FLOAT_OOB_FILL_NONE = 0 (zeros)
+      const int rc = encode(&tmap, 0, 2, (void*)((const uint8_t*)d_data + c0 * cell_size), dims, strides, box, estr, 0, 0, 0, 0);
+      if (rc != 0) return fail(ctx, CDX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", rc);
+      k_hash_cells_tma<<<grid_for(nc), CDX_BLOCK, smem, st>>>(tmap, nc, (uint32_t)cell_size, d_out + 32 * c0);
+      ctx->launches++;
+      CU_TRY(ctx, cudaGetLastError());
+    }
+    return CDX_OK;
   }
-  ctx->launches++;
-  CU_TRY(ctx, cudaGetLastError());
+  const size_t max_cells = (size_t)1 << 30;                                  // keeps the grid below 2^31 CTAs
+  for (size_t c0 = 0; c0 < n_cells; c0 += max_cells) {
+    const size_t nc = n_cells - c0 < max_cells ? n_cells - c0 : max_cells;
+    k_hash_cells<<<grid_for(nc), CDX_BLOCK, 0, st>>>((const uint32_t*)((const uint8_t*)d_data + c0 * cell_size), nc, (uint32_t)(cell_size / 4),
+                                                    d_out + 32 * c0);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+  }
   return CDX_OK;
 }
 
@@ -408,10 +428,12 @@ static int check_shape(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t bl
 }
 
 // allocate a slot handle and lay out its layers; on success the caller fills forest[0] and calls build_trees
+// n_local_blocks == 0 is an EMPTY SHARD (a rank that got no chunk of a small slot): it holds nothing below top_level, takes part
+// in the exchange with zero nodes and still gets the replicated top tree; only the sharded entry points create one.
 static int slot_alloc(cdx_ctx* ctx, uint64_t n_local_blocks, size_t cell_size, size_t block_size, uint64_t first_block,
-                      uint64_t n_total_blocks, int top_level, cudaStream_t st, cdx_slot** out) {
+                      uint64_t n_total_blocks, int top_level, cudaStream_t st, cdx_slot** out, bool allow_empty = false) {
   const uint64_t cpb = block_size / cell_size;
-  if (n_total_blocks == 0 || n_local_blocks == 0 || first_block + n_local_blocks > n_total_blocks)
+  if (n_total_blocks == 0 || (n_local_blocks == 0 && !allow_empty) || first_block + n_local_blocks > n_total_blocks)
     return fail(ctx, CDX_ERR_RANGE, "block range [%llu,+%llu) outside slot of %llu blocks", (unsigned long long)first_block,
                 (unsigned long long)n_local_blocks, (unsigned long long)n_total_blocks);
   cdx_slot* s = new (std::nothrow) cdx_slot();
@@ -440,8 +462,9 @@ static int slot_alloc(cdx_ctx* ctx, uint64_t n_local_blocks, size_t cell_size, s
     s->slot_depth = (uint32_t)s->width.size() - 1;
   }
   if (top_level < 0 || (uint32_t)top_level > s->slot_depth || (n_total_blocks == 1 && top_level != 0)) {
+    const uint32_t depth = s->slot_depth;
     delete s;
-    return fail(ctx, CDX_ERR_RANGE, "top_level %d outside 0..%u", top_level, s->slot_depth);
+    return fail(ctx, CDX_ERR_RANGE, "top_level %d outside 0..%u", top_level, depth);
   }
   s->top_level = (uint32_t)top_level;
   const uint64_t align = 1ull << top_level;
@@ -470,7 +493,7 @@ static int slot_alloc(cdx_ctx* ctx, uint64_t n_local_blocks, size_t cell_size, s
     l_off.push_back(low_nodes);
     low_nodes += s->low_count[l];
   }
-  cudaError_t e = cudaMallocAsync((void**)&s->d_forest, 32 * forest_nodes, st);
+  cudaError_t e = forest_nodes ? cudaMallocAsync((void**)&s->d_forest, 32 * forest_nodes, st) : cudaSuccess;
   if (e == cudaSuccess && low_nodes) e = cudaMallocAsync((void**)&s->d_low, 32 * low_nodes, st);
   if (e != cudaSuccess) {
     cdx_slot_free(s);
@@ -487,6 +510,7 @@ static int slot_alloc(cdx_ctx* ctx, uint64_t n_local_blocks, size_t cell_size, s
 static int build_local_trees(cdx_slot* s) {
   cdx_ctx* ctx = s->ctx;
   const bool singles = (s->block_size / s->cell_size) == 1;
+  if (s->n_local_cells == 0) return CDX_OK;                                  // empty shard
   if (singles) {
     LAUNCH(ctx, k_merkle_level, s->n_local_cells, s->stream, s->forest[0], (size_t)s->n_local_cells, s->forest[1], 1u, 1);
   } else {
@@ -612,8 +636,9 @@ static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   }
   const size_t n_blocks = n_bytes / block_size;
   if (whole_slot) n_total_blocks = n_blocks;
-  // Tile = 256 MiB: 131 072 cells of 2 KiB, i.e. one full wave of the cell-sponge kernel on 148 SMs (7 CTAs of 128
-  // threads per SM at 70 registers); smaller tiles leave SMs idle, larger ones only add exposed first-copy latency.
+  // Tile = 256 MiB: 131 072 cells of 2 KiB, about one full wave of the cell-sponge kernel on 148 SMs (the resident
+  // CTAs per SM are set by CDX_TMA_MIN_CTAS in kernels.cuh); smaller tiles leave SMs idle, larger ones only add exposed
+  // first-copy latency.
   // Slots below 1 GiB are cut in four so that the copy still overlaps.
   size_t tile_bytes_target = (size_t)256 << 20;
   if (n_bytes < ((size_t)1 << 30)) tile_bytes_target = n_bytes / 4 > ((size_t)16 << 20) ? n_bytes / 4 : ((size_t)16 << 20);
@@ -786,17 +811,31 @@ extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t off
   if (rc) return rc;
   const int fd = open(path, O_RDONLY);
   if (fd < 0) return fail(ctx, CDX_ERR_ARG, "cannot open slot data file `%s`", path);
-  ChunkFill fill = [fd, offset](uint8_t* dst, uint64_t off, size_t len) {
+  // A read error is not an end of file: EINTR is retried, anything else is recorded (the fill runs on worker threads) and
+  // fails the commit; only a true EOF zero-fills, like the reference's ignored short reads (slot.nim:64-65).
+  std::atomic<int> io_errno{0};
+  ChunkFill fill = [fd, offset, &io_errno](uint8_t* dst, uint64_t off, size_t len) {
     size_t pos = 0;
     while (pos < len) {
       const ssize_t got = pread(fd, dst + pos, len - pos, (off_t)(offset + off + pos));
-      if (got <= 0) break;                                                  // EOF or error: the rest reads as zeros (slot.nim:64-65)
+      if (got < 0) {
+        if (errno == EINTR) continue;
+        int expected = 0;
+        io_errno.compare_exchange_strong(expected, errno);
+        break;
+      }
+      if (got == 0) break;                                                  // EOF: the rest reads as zeros
       pos += (size_t)got;
     }
     if (pos < len) memset(dst + pos, 0, len - pos);
   };
   rc = commit_staged(ctx, n_bytes, cell_size, block_size, 0, 0, 0, true, fill, out);
   close(fd);
+  if (rc == CDX_OK && io_errno.load() != 0) {
+    cdx_slot_free(*out);
+    *out = nullptr;
+    return fail(ctx, CDX_ERR_ARG, "reading slot data file `%s` failed: %s", path, strerror(io_errno.load()));
+  }
   return rc;
 }
 
@@ -1185,22 +1224,26 @@ extern "C" int cdx_probe_imad_rate(cdx_ctx* ctx, int kind, double* ops_per_secon
   CU_TRY(ctx, sink.alloc(4, ctx->stream));
   const unsigned blocks = (unsigned)ctx->sm_count * 8, threads = 256;
   const uint32_t iters = 8192;
-  cudaEvent_t e0, e1;
-  CU_TRY(ctx, cudaEventCreate(&e0));
-  CU_TRY(ctx, cudaEventCreate(&e1));
+  struct Events {                                   // destroyed on every exit path
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+    }
+  } ev;
+  CU_TRY(ctx, cudaEventCreate(&ev.e0));
+  CU_TRY(ctx, cudaEventCreate(&ev.e1));
   float best = 0.f;
   for (int rep = 0; rep < 4; ++rep) {   // rep 0 is the warm-up
-    CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(ev.e0, ctx->stream));
     k_probe_imad<<<blocks, threads, 0, ctx->stream>>>(kind, iters, 12345u + rep, (uint32_t*)sink.p);
     ctx->launches++;
-    CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(ev.e1, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
-    CU_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ev.e0, ev.e1));
     if (rep > 0 && (best == 0.f || ms < best)) best = ms;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   const double ops = (double)blocks * threads * iters * CDX_PROBE_OPS_PER_ITER;
   *ops_per_second = ops / (best * 1e-3);
   if (elapsed_ms) *elapsed_ms = best;

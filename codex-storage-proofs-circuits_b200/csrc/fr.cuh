@@ -30,6 +30,7 @@
 // contains no host arithmetic.
 #pragma once
 #include <stdint.h>
+#include "fr_reduce_tab.cuh"
 
 #if defined(__CUDACC__)
 #define CDX_HD __host__ __device__ __forceinline__
@@ -66,6 +67,19 @@ struct Fr {
 #define CDX_R2_INIT {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}
 // R mod r = Montgomery form of 1
 #define CDX_ONE_INIT {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}
+
+// Table-driven reduction (reduce_tab below).  The 4 KB table lives in global memory and is copied into shared memory by
+// every CTA that runs field arithmetic (load_reduce_tab(), first statement of each kernel): the row a thread needs
+// depends on its own value, which constant memory would serialise and shared memory serves in two LDS.128.
+#if defined(__CUDACC__)
+static __device__ const uint32_t g_reduce_tab[8 * CDX_REDUCE_TAB_ENTRIES] = CDX_REDUCE_TAB_INIT;
+__shared__ uint4 s_reduce_tab[2 * CDX_REDUCE_TAB_ENTRIES];
+static __device__ __forceinline__ void load_reduce_tab() {
+  for (uint32_t i = threadIdx.x; i < 2 * CDX_REDUCE_TAB_ENTRIES; i += blockDim.x)
+    s_reduce_tab[i] = reinterpret_cast<const uint4*>(g_reduce_tab)[i];
+  __syncthreads();
+}
+#endif
 
 #if defined(__CUDA_ARCH__)
 // ---------------------------------------------------------------------------------------------------------
@@ -268,6 +282,35 @@ CDX_D void sub_modulus(uint32_t* d, const uint32_t* a) {
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "n"(CDX_N0),
         "n"(CDX_N1), "n"(CDX_N2), "n"(CDX_N3), "n"(CDX_N4), "n"(CDX_N5), "n"(CDX_N6), "n"(CDX_N7));
 }
+
+// r = a - b mod 2^256 (callers guarantee a >= b, or a + 2^256 >= b when the 257th bit is implied: see reduce_tab)
+CDX_D void sub256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  asm("sub.cc.u32 %0, %8, %16; subc.cc.u32 %1, %9, %17; subc.cc.u32 %2, %10, %18; subc.cc.u32 %3, %11, %19;"
+      "subc.cc.u32 %4, %12, %20; subc.cc.u32 %5, %13, %21; subc.cc.u32 %6, %14, %22; subc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+        "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+
+// r = a + b mod 2^256, returns the carry out (bit 256 of the sum)
+CDX_D uint32_t add256c(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t c;
+  asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
+      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24;"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+        "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return c;
+}
+
+// index of a 257-bit value (carry : limb 7) in the reduction table: its top 7 bits
+CDX_D uint32_t reduce_tab_index(uint32_t top_limb, uint32_t carry) { return __funnelshift_l(top_limb, carry, 6); }
+// row `idx` of the reduction table, from the CTA's shared-memory copy (two 16-byte loads on the otherwise idle LSU pipe)
+CDX_D void reduce_tab_row(uint32_t* t, uint32_t idx) {
+  const uint4 a = s_reduce_tab[2 * idx], b = s_reduce_tab[2 * idx + 1];
+  t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w;
+}
 #elif defined(CDX_HOST_EMUL)
 }  // namespace cdx
 #include "fr_rows_host.h"  // tests/host_emul: C emulation of the primitives above (unit tests only)
@@ -289,6 +332,10 @@ uint32_t shl1_funnel(uint32_t, uint32_t);
 void mont_merge(uint32_t*, const uint32_t*, const uint32_t*);
 void add256(uint32_t*, const uint32_t*, const uint32_t*);
 void sub_modulus(uint32_t*, const uint32_t*);
+void sub256(uint32_t*, const uint32_t*, const uint32_t*);
+uint32_t add256c(uint32_t*, const uint32_t*, const uint32_t*);
+uint32_t reduce_tab_index(uint32_t, uint32_t);
+void reduce_tab_row(uint32_t*, uint32_t);
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
@@ -360,6 +407,25 @@ CDX_D Fr reduce_once(const Fr& a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) r.l[i] = lt ? a.l[i] : d.l[i];
   return r;
+}
+
+// Table-driven reduction: any v < 2^257 (given as 256 bits + the carry out of the add that produced it) -> the
+// congruent value v - q r in [0, r + 2^250) = [0, 1.0827 r), q = floor(floor(v / 2^250) * 2^250 / r) read from a table by the
+// top 7 bits of v.  One shift, two shared-memory loads and ONE subtraction chain: no trial subtraction, no select.
+// "B" below is this bound, 1.0827 r.
+CDX_D Fr reduce_tab(const Fr& v, uint32_t carry) {
+  uint32_t t[8];
+  reduce_tab_row(t, reduce_tab_index(v.l[7], carry));
+  Fr r;
+  sub256(r.l, v.l, t);
+  return r;
+}
+
+// a + b, 257-bit sum -> [0, B)
+CDX_D Fr add_reduce(const Fr& a, const Fr& b) {
+  Fr s;
+  const uint32_t c = add256c(s.l, a.l, b.l);
+  return reduce_tab(s, c);
 }
 
 // a + b without reduction (caller guarantees a + b < 2^256)

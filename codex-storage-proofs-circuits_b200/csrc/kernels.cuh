@@ -26,11 +26,20 @@ static __device__ __forceinline__ void st_felt(uint8_t* p, const Fr& v) {
 }
 
 #ifndef CDX_BLOCK
-#define CDX_BLOCK 128
+#define CDX_BLOCK 256
+#endif
+
+// first statement of every kernel that does field arithmetic: the CTA's copy of the reduction table (fr.cuh), before any
+// thread can leave
+#if CDX_TABRED
+#define CDX_KERNEL_PROLOGUE() load_reduce_tab()
+#else
+#define CDX_KERNEL_PROLOGUE() ((void)0)
 #endif
 
 // K1: n independent permutations (BASELINE config 2).           Permutation.hs:40-45
 __global__ void __launch_bounds__(CDX_BLOCK) k_permutation_batch(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr x = to_mont(ld_felt(in + 96 * i)), y = to_mont(ld_felt(in + 96 * i + 32)), z = to_mont(ld_felt(in + 96 * i + 64));
@@ -43,6 +52,7 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_permutation_batch(const uint8_t* 
 // sponge over field elements, one sponge per thread.             Sponge.hs:13-43
 __global__ void __launch_bounds__(CDX_BLOCK) k_sponge_felts(const uint8_t* __restrict__ elems, size_t n_items, uint32_t len, int rate,
                                                             uint8_t* __restrict__ out) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) return;
   const uint8_t* base = elems + (size_t)32 * len * i;
@@ -54,6 +64,7 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_sponge_felts(const uint8_t* __res
 // sizes).  Cells are 4-byte aligned and a multiple of 4 bytes long.        blocks/bn254.nim:23-29, Slot.hs:222-228
 __global__ void __launch_bounds__(CDX_BLOCK) k_hash_cells(const uint32_t* __restrict__ data, size_t n_cells, uint32_t cell_words,
                                                           uint8_t* __restrict__ out) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cells) return;
   AlignedWords ld{data + (size_t)cell_words * i, cell_words};
@@ -66,16 +77,17 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_hash_cells(const uint32_t* __rest
 // (cp.async.bulk.tensor.2d -> SASS UTMALDG) issued by one elected lane into a ring of CDX_RING_SLOTS boxes of
 // 32 rows x 32 B, two segments ahead of the sponge.  One mbarrier per (warp, ring slot): expect_tx = 1024 B, the phase
 // completes when the box has landed (rows past the end of the slot are zero-filled by the TMA unit and still counted).
-// Lane l only ever reads row l, and a box is overwritten only after the step that last read it, so there is no
-// cross-thread hand-shake beyond the warp being convergent.
+// Lane l only ever reads row l, and a box is overwritten only after the step that last read it: begin_step opens with a
+// __syncwarp(), which orders every lane's reads of step j-1 before the elected lane's refill.
 //   HBM traffic: each 32-byte sector of the slot is fetched exactly once.
 #ifndef CDX_RING_SLOTS
 #define CDX_RING_SLOTS 6
 #endif
-// resident CTAs per SM the cell kernel is compiled for: 8 x 128 threads caps it at 64 registers (measured 0.8 % faster than
-// the 68 registers ptxas takes when left alone, at 7 CTAs per SM)
+// resident CTAs per SM the cell kernel is compiled for: 3 x 256 threads = 24 warps at 80 registers, no spills.  With the
+// table-driven reduction the kernel is insensitive to occupancy (same-box sweep, profiles/r2_sweep_occupancy.txt: 16 to 32
+// warps per SM within 0.2 %); this point was the fastest and leaves room for the 4 KB reduction table next to the rings.
 #ifndef CDX_TMA_MIN_CTAS
-#define CDX_TMA_MIN_CTAS 8
+#define CDX_TMA_MIN_CTAS 3
 #endif
 #define CDX_SEG_BYTES 32u
 #define CDX_BOX_BYTES (32u * CDX_SEG_BYTES)
@@ -108,6 +120,9 @@ struct RowRing {
   // step j of the sponge reads padded-stream bytes [62 j, 62 j + 68): make those segments resident, keep two ahead
   __device__ __forceinline__ void begin_step(uint32_t j) const {
     const int issued = want_at((int)j - 1), want = want_at((int)j);
+    // every lane has finished reading the boxes of step j-1 (and has passed its waits on their barriers) before the
+    // elected lane re-arms a barrier and lets the async proxy overwrite a box: convergence is not assumed
+    __syncwarp();
     if ((threadIdx.x & 31u) == 0) {
       const uint32_t row0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);          // first cell (tensor row) of this warp
       for (int g = issued + 1; g <= want; ++g) {
@@ -150,6 +165,7 @@ struct alignas(64) TensorMap2D {   // layout-compatible with CUtensorMap (128 op
 __global__ void __launch_bounds__(CDX_BLOCK, CDX_TMA_MIN_CTAS) k_hash_cells_tma(const __grid_constant__ TensorMap2D tmap, size_t n_cells, uint32_t cell_bytes,
                                                               uint8_t* __restrict__ out) {
   extern __shared__ uint8_t smem[];
+  CDX_KERNEL_PROLOGUE();
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t warp_first = i - lane;
@@ -174,6 +190,7 @@ __global__ void __launch_bounds__(CDX_BLOCK, CDX_TMA_MIN_CTAS) k_hash_cells_tma(
 // byte strings of arbitrary length/alignment (test-vector suite: n = 0..80).   testvectors.nim:41-46
 __global__ void __launch_bounds__(CDX_BLOCK) k_hash_bytes_any(const uint8_t* __restrict__ data, size_t n_items, uint32_t len,
                                                               uint8_t* __restrict__ out) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) return;
   AnyBytes ld{data + (size_t)len * i, len};
@@ -183,6 +200,7 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_hash_bytes_any(const uint8_t* __r
 // keyed compression batch.                                       Merkle.hs:202-203, merkle/bn254.nim:18
 __global__ void __launch_bounds__(CDX_BLOCK) k_compress_batch(const uint8_t* __restrict__ x, const uint8_t* __restrict__ y,
                                                               const uint32_t* __restrict__ keys, size_t n, uint8_t* __restrict__ out) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   st_felt(out + 32 * i, from_mont(compress_keyed(to_mont(ld_felt(x + 32 * i)), to_mont(ld_felt(y + 32 * i)), keys[i] & 3u)));
@@ -194,6 +212,7 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_compress_batch(const uint8_t* __r
 // singles != 0: every input is a one-leaf tree of its own -> out[i] = compress(in[i], 0, 3) (Merkle.hs:73).
 __global__ void __launch_bounds__(CDX_BLOCK) k_merkle_level(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out,
                                                             uint32_t bottom, int singles) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t n_out = singles ? n : (n + 1) / 2;
   if (i >= n_out) return;
@@ -268,6 +287,7 @@ __global__ void k_gather_paths(PathPlan plan, const uint64_t* __restrict__ cells
 __global__ void __launch_bounds__(CDX_BLOCK) k_reconstruct_roots(const uint8_t* __restrict__ leaves, const uint64_t* __restrict__ indices,
                                                                  uint64_t n_leaves, const uint8_t* __restrict__ paths, uint32_t stride,
                                                                  uint32_t depth, size_t n, uint8_t* __restrict__ out) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t j = indices[i], m = n_leaves;
@@ -290,6 +310,7 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_reconstruct_roots(const uint8_t* 
 // entropies: n_challenges x 32 B, root: 32 B (both canonical), out[ch * n_samples + c-1].
 __global__ void k_cell_indices(const uint8_t* __restrict__ entropies, const uint8_t* __restrict__ root, uint64_t mask, uint32_t n_samples,
                                size_t total, uint64_t* __restrict__ out) {
+  CDX_KERNEL_PROLOGUE();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t ch = i / n_samples;

@@ -34,6 +34,50 @@ CDX_D Fr sponge_iv(int rate) {
   return to_mont(a);
 }
 
+#ifndef CDX_TABRED
+#define CDX_TABRED 1
+#endif
+
+#if CDX_TABRED
+// Range discipline of the permutation (units of r; B = 1 + 2^250/r = 1.0827 is what reduce_tab returns):
+//   state words are < B at every round boundary;
+//   S-box input t = w + c < B + 1 = 2.083 (mont_sqr wants < 2.14);  t^2 < 1.82,  t^4 < 1.63,  t^5 < 1.64 -- left unreduced;
+//   the mixes add up to 2x' + y + z < 6.6 resp. x' + y + 3z < 6.0, i.e. at most 257 bits (2^257 = 10.6 r), and every new
+//   state word goes through ONE table reduction (reduce_tab, fr.cuh) instead of a chain of conditional subtractions.
+
+// x^5 with x < 2.14 r; result < 1.64 r                               Permutation.hs:14-17
+CDX_D Fr sbox(const Fr& x) {
+  Fr x2 = mont_sqr(x);
+  Fr x4 = mont_sqr(x2);
+  return mont_mul(x4, x);
+}
+
+// (x,y,z) <- (x+s, y+s, z+s), s = x+y+z; inputs < 1.64 r, outputs < B     Permutation.hs:35-36 and the external-round mix :28-33
+CDX_D void mix_external(Fr& x, Fr& y, Fr& z) {
+  const Fr s = add_lazy(add_lazy(x, y), z);       // < 4.92 r: fits 256 bits
+  x = add_reduce(x, s);                           // < 6.56 r: 257 bits
+  y = add_reduce(y, s);
+  z = add_reduce(z, s);
+}
+
+// internal-round mix with x already through its S-box (x < 1.64 r; y, z < B)   Permutation.hs:19-26, matrix [[2,1,1],[1,2,1],[1,1,3]]
+CDX_D void mix_internal(Fr& x, Fr& y, Fr& z) {
+  const Fr s = add_lazy(x, add_lazy(y, z));       // < 3.81 r
+  x = add_reduce(x, s);                           // 2x + y + z < 5.45 r
+  y = reduce_tab(add_lazy(y, s), 0u);             // x + 2y + z < 4.89 r: no carry
+  z = add_reduce(z, add_lazy(z, s));              // x + y + 3z < 5.97 r
+}
+
+// absorb one element into a state word: w + m*R mod r.  m standard form, any value < 2^256; w < B; result < B
+CDX_D Fr absorb(const Fr& w, const Fr& m) {
+  const Fr r2 = {CDX_R2_INIT};
+  return add_reduce(w, mont_mul(r2, m));          // R2 < r is the row operand: product < 2r whatever m
+}
+CDX_D Fr absorb_one(const Fr& w) {
+  const Fr one = {CDX_ONE_INIT};
+  return add_reduce(w, one);
+}
+#else
 // x^5 with x < 2r; result < r                                       Permutation.hs:14-17
 CDX_D Fr sbox(const Fr& x) {
   Fr x2 = mont_sqr(x);
@@ -57,7 +101,14 @@ CDX_D void mix_internal(Fr& x, Fr& y, Fr& z) {
   z = add_mod(dbl_mod(z), s);
 }
 
-// state words < r in, < r out                                       Permutation.hs:40-45
+CDX_D Fr absorb(const Fr& w, const Fr& m) { return add_mod(w, to_mont(m)); }
+CDX_D Fr absorb_one(const Fr& w) {
+  const Fr one = {CDX_ONE_INIT};
+  return add_mod(w, one);
+}
+#endif
+
+// state words < B (1.083 r) in, < B out                             Permutation.hs:40-45
 // Four S-box instances in the instruction stream: one in the internal-round loop (56 of the 80 S-box evaluations,
 // nothing else in its body) and the three independent ones of an external round, in one loop body shared by all
 // eight external rounds (the `half` loop runs it before and after the internal rounds).  With the first, larger
@@ -147,16 +198,15 @@ template <class LoadWord>
 CDX_D Fr sponge2_bytes(const LoadWord& ld, uint32_t len_bytes) {
   const uint32_t n = n_chunks(len_bytes);
   const uint32_t n_perm = n / 2u + 1u;
-  const Fr one = {CDX_ONE_INIT};
   Fr s0 = fr_zero(), s1 = fr_zero(), s2 = sponge_iv(2);
 #pragma unroll 1
   for (uint32_t j = 0; j < n_perm; ++j) {
     const uint32_t k = 2u * j;
     ld.begin_step(j);                 // step j reads padded-stream bytes [62 j, 62 j + 68)
-    if (k < n) s0 = add_mod(s0, to_mont(read_chunk(ld, k)));
-    else s0 = add_mod(s0, one);
-    if (k + 1 < n) s1 = add_mod(s1, to_mont(read_chunk(ld, k + 1)));
-    else if (k + 1 == n) s1 = add_mod(s1, one);
+    if (k < n) s0 = absorb(s0, read_chunk(ld, k));
+    else s0 = absorb_one(s0);
+    if (k + 1 < n) s1 = absorb(s1, read_chunk(ld, k + 1));
+    else if (k + 1 == n) s1 = absorb_one(s1);
     permute(s0, s1, s2);
   }
   return s0;
@@ -166,17 +216,16 @@ CDX_D Fr sponge2_bytes(const LoadWord& ld, uint32_t len_bytes) {
 //                                                                   Sponge.hs:13-43
 template <class GetElem>
 CDX_D Fr sponge_elems(GetElem get, uint32_t n, int rate) {
-  const Fr one = {CDX_ONE_INIT};
   Fr s0 = fr_zero(), s1 = fr_zero(), s2 = sponge_iv(rate);
   const uint32_t n_perm = rate == 1 ? n + 1u : n / 2u + 1u;
 #pragma unroll 1
   for (uint32_t j = 0; j < n_perm; ++j) {
     const uint32_t k = rate == 1 ? j : 2u * j;
-    if (k < n) s0 = add_mod(s0, to_mont(get(k)));
-    else s0 = add_mod(s0, one);
+    if (k < n) s0 = absorb(s0, get(k));
+    else s0 = absorb_one(s0);
     if (rate == 2) {
-      if (k + 1 < n) s1 = add_mod(s1, to_mont(get(k + 1)));
-      else if (k + 1 == n) s1 = add_mod(s1, one);
+      if (k + 1 < n) s1 = absorb(s1, get(k + 1));
+      else if (k + 1 == n) s1 = absorb_one(s1);
     }
     permute(s0, s1, s2);
   }

@@ -134,7 +134,8 @@ inline void add256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   emul::CC c;
   r[0] = c.add_cc(a[0], b[0]);
   for (int k = 1; k < 7; ++k) r[k] = c.addc_cc(a[k], b[k]);
-  r[7] = c.addc(a[7], b[7]);
+  r[7] = c.addc_cc(a[7], b[7]);
+  if (c.cf) __builtin_trap();          // add_lazy's contract: the sum fits 256 bits
 }
 
 inline void sub_modulus(uint32_t* d, const uint32_t* a) {
@@ -142,5 +143,35 @@ inline void sub_modulus(uint32_t* d, const uint32_t* a) {
   d[0] = c.sub_cc(a[0], kModHost[0]);
   for (int k = 1; k < 8; ++k) d[k] = c.subc_cc(a[k], kModHost[k]);
   if ((c.cf & 1u) != (d[7] >> 31)) __builtin_trap();   // the caller reads the borrow off the sign bit: only valid for a < 2r
+}
+static const uint32_t kReduceTabHost[8 * CDX_REDUCE_TAB_ENTRIES] = CDX_REDUCE_TAB_INIT;
+
+inline void sub256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  emul::CC c;
+  r[0] = c.sub_cc(a[0], b[0]);
+  for (int k = 1; k < 8; ++k) r[k] = c.subc_cc(a[k], b[k]);
+  // reduce_tab's contract: the difference is < r + 2^250, whatever borrow the implied 257th bit absorbed
+  static const uint32_t bound[8] = {CDX_N0, CDX_N1, CDX_N2, CDX_N3, CDX_N4, CDX_N5, CDX_N6, CDX_N7 + (1u << 26)};
+  for (int k = 7; k >= 0; --k) {
+    if (r[k] < bound[k]) break;
+    if (r[k] > bound[k] || k == 0) __builtin_trap();
+  }
+}
+
+// the add256 emulation above silently wraps; this one is for sums that are allowed to reach 257 bits
+inline uint32_t add256c(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  emul::CC c;
+  r[0] = c.add_cc(a[0], b[0]);
+  for (int k = 1; k < 8; ++k) r[k] = c.addc_cc(a[k], b[k]);
+  return c.cf;
+}
+
+inline uint32_t reduce_tab_index(uint32_t top_limb, uint32_t carry) {
+  if (carry > 1) __builtin_trap();
+  return (carry << 6) | (top_limb >> 26);
+}
+inline void reduce_tab_row(uint32_t* t, uint32_t idx) {
+  if (idx >= CDX_REDUCE_TAB_ENTRIES) __builtin_trap();
+  for (int k = 0; k < 8; ++k) t[k] = kReduceTabHost[8 * idx + k];
 }
 }  // namespace cdx
