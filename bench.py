@@ -7,8 +7,17 @@
 A "step" is one commitment of the workload: every 2048-byte cell through the Poseidon2 rate-2 sponge, every 64 KiB
 block tree, the slot tree, and the 32-byte root read back.  Workload at N = 1: BASELINE.json configs[2], a single
 10 GiB synthetic slot (163 840 blocks, not a power of two).  At N > 1 each rank holds 10 GiB of one N x 10 GiB slot
-(weak scaling), commits its block range on its own GPU, and one NCCL all-gather of the level-15 sub-tree roots
-(5 x 32 B per rank) feeds the replicated top tree.
+(weak scaling) and commits it through ONE C-ABI call, cdx_slot_commit_sharded_*: its block range on its own GPU, one NCCL
+collective inside the library for the level-15 sub-tree roots (5 x 32 B per rank), the replicated top tree.  torch
+supplies the process group that broadcasts the library's 128-byte communicator id, the barrier and the device buffers --
+nothing on the data path.
+
+Beside the headline the line carries (each outside the headline's timed region, each with its own timing):
+  N = 1   small_slots      BASELINE configs[0] (eleven 4 MiB fake-data slots + dataset root) through the batched entry point,
+                           and 1000 x 4 MiB slots batched vs one by one
+  N > 1   config4_strong   BASELINE configs[3]: ONE 100 GiB slot split over the ranks, root checked against the known value
+          sharded_root_check  rank 0 re-commits the whole N x 10 GiB slot alone and compares roots
+  N = 8   config5          BASELINE configs[4] at quarter scale: 250 slots (non-power-of-two), 0.25-25 GiB, cdx_dataset_commit
 
   value     whole-job GB/s with the slot bytes already resident in HBM (CUDA events, max over ranks)
   e2e       the same through the host-buffer C-ABI call (pinned host slot -> cdx_slot_commit[_range]_host), H2D of
@@ -72,7 +81,8 @@ def make_config(args, world: int, n_total_blocks: int, top_level: int, ranges) -
                          f"single {args.slot_gib:g} GiB-per-GPU synthetic slot") +
                         f" ({n_total_blocks} blocks of 64 KiB, 2048-byte cells): cell sponge + block trees + slot tree + root",
             "bytes_per_step": n_total_blocks * BLOCK, "cell_size": CELL, "block_size": BLOCK, "seed": SEED,
-            "parallelism": "1 GPU" if world == 1 else f"{world} ranks x block-range shards, all-gather of level-{top_level} roots",
+            "parallelism": "1 GPU" if world == 1 else f"{world} ranks x block-range shards, level-{top_level} roots combined by one NCCL collective "
+                                                       "inside cdx_slot_commit_sharded_*",
             "l2": f"inputs ({per_gpu / 2**30:.1f} GiB per GPU) are larger than L2; no flush needed"}
 
 
@@ -166,29 +176,44 @@ class ClockSampler:
 
 def run_reference(args) -> None:
     """The reference arm: the path's CPU implementation on the box's host cores.  The Nim reference cannot be built
-    here (no nim/nimble; constantine and nim-poseidon2 are un-vendored), so this is the oracle port, all threads."""
+    here (no nim/nimble; constantine and nim-poseidon2 are un-vendored), so this is the oracle port, all threads, compiled
+    on this machine with -O3 -march=native (dedicated squaring, MULX/ADX through unsigned __int128)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import coracle
+    native = coracle.use_native()
     threads = host_threads()
+    # one step = one commitment of a bounded prefix of the workload's synthetic slot; 1 GiB unless the whole run would
+    # exceed ~3 minutes on this host, in which case the prefix shrinks (never below 256 MiB) -- the real size is reported
+    probe_s, _ = time_oracle_commit(64 << 20, threads)
+    rate = (64 << 20) / probe_s
+    budget_s = 180.0
     sample = args.ref_sample_mib << 20
-    for _ in range(args.warmup if args.warmup < 2 else 1):      # CPU needs no real warm-up; one pass touches the pages
-        time_oracle_commit(sample, threads)
+    while sample > (256 << 20) and sample * (args.steps + 1) / rate > budget_s:
+        sample //= 2
+    time_oracle_commit(sample, threads)                      # one untimed pass (touches the pages); a CPU needs no more warm-up
     t = 0.0
     for _ in range(args.steps):
         dt, _ = time_oracle_commit(sample, threads)
         t += dt
     gbs = sample * args.steps / t / 1e9
     n_total_blocks, top_level, ranges, scaling = layout(args, args.gpus)
+    cfg = make_config(args, args.gpus, n_total_blocks, top_level, ranges)
+    cfg["reference_sample"] = (f"each reference step commits the first {sample >> 20} MiB ({sample // BLOCK} blocks) of that slot on "
+                               f"{threads} host threads, not the whole slot: a rate, scaled to the same unit")
+    cfg["reference_sample_bytes"] = sample
     line = {
         "impl": "reference", "metric": "slot commit GB/s (with Poseidon2 perms/s)", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "u64x4 (BN254 Fr, Montgomery)", "data": "synthetic",
-        "config": make_config(args, args.gpus, n_total_blocks, top_level, ranges),
+        "config": cfg,
         "perms_per_s": total_perms(sample // BLOCK) * args.steps / t,
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": f"first {args.ref_sample_mib} MiB of the workload's synthetic slot per step, {threads} threads over blocks; "
-                                   "C restatement of reference/nim/proof_input (Nim toolchain absent)"},
+                         "sample": f"first {sample >> 20} MiB of the workload's synthetic slot per step, {threads} threads over blocks; "
+                                   "C restatement of reference/nim/proof_input (Nim toolchain absent), "
+                                   + ("gcc -O3 -march=native on this host" if native else "portable -O3 -mbmi2 -madx build") +
+                                   ", dedicated squaring"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -204,8 +229,12 @@ def main() -> None:
     ap.add_argument("--total-gib", type=float, default=0.0,
                     help="strong scaling: ONE slot of this many GiB split over the ranks by plan_block_ranges (BASELINE config 4: 100); "
                          "overrides --slot-gib")
-    ap.add_argument("--ref-sample-mib", type=int, default=64, help="bytes per step of the --impl reference CPU run")
-    ap.add_argument("--cpu-sample-mib", type=int, default=256, help="sample committed once for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--ref-sample-mib", type=int, default=1024, help="bytes per step of the --impl reference CPU run (shrinks on slow hosts)")
+    ap.add_argument("--cpu-sample-mib", type=int, default=1024, help="sample committed once for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--no-extras", action="store_true", help="skip small_slots / config4_strong / sharded_root_check / config5")
+    ap.add_argument("--config5", default="auto", choices=["auto", "on", "off"], help="dataset commit (BASELINE configs[4]); auto = only at 8 GPUs")
+    ap.add_argument("--config5-scale", type=float, default=0.25, help="slot sizes are 1-100 GiB times this factor")
+    ap.add_argument("--config5-slots", type=int, default=250)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -238,6 +267,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(local_rank)                      # raises if libcodexcommit.so or the GPU is missing: no fallback
     stream = torch.cuda.ExternalStream(ctx.stream)     # the library's compute stream, so events see its kernels
+    comm = sharded.comm_from_torch(ctx) if world > 1 else None    # the library's own NCCL communicator (cdx_comm_init_rank)
 
     n_total_blocks, top_level, ranges, scaling = layout(args, world)
     first_block, my_blocks = ranges[rank]
@@ -258,8 +288,7 @@ def main() -> None:
             root = slot.root                          # 32-byte D2H, synchronises the stream
             slot.free()
             return root
-        sh = sharded.GpuShard(ctx.slot_commit_range_dev(d_slot.data_ptr(), n_bytes, CELL, BLOCK, first_block, n_total_blocks, top_level))
-        sharded.exchange_subtree_roots(sh, n_total_blocks, top_level, ranges)
+        sh = ctx.slot_commit_sharded_dev(comm, d_slot.data_ptr(), n_bytes, CELL, BLOCK, first_block, n_total_blocks, top_level)
         root = sh.root
         sh.free()
         return root
@@ -375,8 +404,7 @@ def main() -> None:
                 r = slot.root
                 slot.free()
                 return r
-            sh = sharded.GpuShard(ctx.slot_commit_range_host(h_np, CELL, BLOCK, first_block, n_total_blocks, top_level))
-            sharded.exchange_subtree_roots(sh, n_total_blocks, top_level, ranges)
+            sh = ctx.slot_commit_sharded_host(comm, h_np, n_bytes, CELL, BLOCK, first_block, n_total_blocks, top_level)
             r = sh.root
             sh.free()
             return r
@@ -387,15 +415,21 @@ def main() -> None:
         assert r2 == root, "host-buffer path and resident path disagree on the slot root"
         e2e = {"value": total_bytes * args.steps / e2e_wall / 1e9, "unit": "GB/s", "h2d_bytes_per_step": total_bytes, "d2h_bytes_per_step": 32 * world,
                "ms_per_step": 1e3 * e2e_wall / args.steps,
-               "api": "cdx_slot_commit_host" if world == 1 else "cdx_slot_commit_range_host + NCCL all-gather + cdx_slot_set_top_dev",
+               "api": "cdx_slot_commit_host + cdx_slot_root" if world == 1 else
+                      "cdx_slot_commit_sharded_host + cdx_slot_root (NCCL inside libcodexcommit.so; communicator from cdx_comm_init_rank)",
                "timing": "wall clock bracketed by barrier + cudaDeviceSynchronize, max over ranks"}
         del h_slot
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import coracle
+        native = coracle.use_native()                         # -O3 -march=native, compiled on this host
         threads = host_threads()
         sample = min(args.cpu_sample_mib << 20, n_bytes)
+        probe_s, _ = time_oracle_commit(64 << 20, threads)
+        while sample > (256 << 20) and sample / ((64 << 20) / probe_s) > 30.0:     # keep the leg near 10-30 s on slow hosts
+            sample //= 2
         dt, cpu_root = time_oracle_commit(sample, threads)
         # the sample doubles as a parity check at bench size: GPU root of the same prefix must equal the oracle's
         with ctx.slot_commit_dev(d_slot.data_ptr(), sample, CELL, BLOCK) as s:
@@ -403,7 +437,15 @@ def main() -> None:
         cpu = {"value": sample / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
                "perms_per_s": total_perms(sample // BLOCK) / dt,
                "sample": f"first {sample >> 20} MiB of the same synthetic slot, one commitment, {threads} threads over blocks "
-                         "(C restatement of reference/nim/proof_input; Nim toolchain absent); root checked equal to the GPU's"}
+                         "(C restatement of reference/nim/proof_input; Nim toolchain absent; "
+                         + ("gcc -O3 -march=native on this host" if native else "portable build") + ", dedicated squaring); root checked equal to the GPU's"}
+
+    # ---- the other BASELINE configs, each with its own timing, outside the headline's timed region ----
+    extras = {}
+    del d_slot
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        extras = run_extras(args, torch, dist, pkg, ctx, comm, stream, rank, world, value, timed, barrier)
 
     if rank == 0:
         line = {
@@ -416,12 +458,146 @@ def main() -> None:
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "perm_batch_2^20": perm_batch,
         }
+        line.update(extras)
+        if "sharded_root_check" in extras:
+            extras["sharded_root_check"]["equals_sharded_root"] = extras["sharded_root_check"]["whole_slot_root_one_gpu"] == hex(root)
+            assert extras["sharded_root_check"]["equals_sharded_root"], "sharded and whole-slot roots differ"
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
+    if comm is not None:
+        comm.destroy()
     if world > 1:
         dist.destroy_process_group()
+
+
+KNOWN_100GIB_ROOT = 0x2df82ef94d66472dbd46bf76aaa677cf31b2a42447b71f1f82be2a9fb524894b     # seed 0xC0DE, committed whole on one GPU in round 1
+CONFIG1_SLOT_ROOT = 16142339001376051487701717049451130483290782524159378806355159917477338192952
+CONFIG1_DATASET_ROOT = 7410604474820069305866101106843319395502234157925946588762357169176803727431
+
+
+def run_extras(args, torch, dist, pkg, ctx, comm, stream, rank, world, weak_value, timed, barrier) -> dict:
+    dataset = importlib.import_module(PKG + ".dataset")
+    capi = pkg.capi
+    out = {}
+
+    if world == 1:
+        # ---- BASELINE configs[0]: eleven 4 MiB fake-data slots, one call, roots read back once ----
+        seeds = [dataset.slot_seed(12345, k) for k in range(11)]
+        ctx.slots_commit_batch_fake(seeds, 2048)
+        t0 = time.perf_counter()
+        roots = ctx.slots_commit_batch_fake(seeds, 2048)
+        dset_root = ctx.merkle_root(roots)
+        t_batch = time.perf_counter() - t0
+        assert roots[3] == CONFIG1_SLOT_ROOT and dset_root == CONFIG1_DATASET_ROOT, "config 1 roots differ from the pinned values"
+        t0 = time.perf_counter()
+        for sd in seeds:
+            with ctx.slot_commit_fake(sd, 2048) as s1:
+                _ = s1.root
+        t_serial = time.perf_counter() - t0
+        # ---- 1000 x 4 MiB synthetic slots: batched vs one by one (data resident) ----
+        n_small, small_bytes = 1000, 4 << 20
+        d_many = torch.empty(n_small * small_bytes, dtype=torch.uint8, device="cuda")
+        for k in range(n_small):
+            ctx.fill_synthetic_dev(dataset.slot_seed(SEED, k), 0, small_bytes, d_many.data_ptr() + k * small_bytes)
+        torch.cuda.synchronize()
+        sizes = [small_bytes] * n_small
+        ctx.slots_commit_batch_dev(d_many.data_ptr(), sizes)
+        t0 = time.perf_counter()
+        broots = ctx.slots_commit_batch_dev(d_many.data_ptr(), sizes)
+        t_b = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sroots = []
+        for k in range(100):
+            with ctx.slot_commit_dev(d_many.data_ptr() + k * small_bytes, small_bytes) as s1:
+                sroots.append(s1.root)
+        t_s = (time.perf_counter() - t0) * n_small / 100
+        assert broots[:100] == sroots, "batched and one-by-one roots differ"
+        out["small_slots"] = {
+            "config1_11x4MiB_fake": {"batched_ms": 1e3 * t_batch, "one_by_one_ms": 1e3 * t_serial, "slot_root_3": hex(roots[3]), "dataset_root": hex(dset_root),
+                                     "roots_match_pinned_values": True, "api": "cdx_slots_commit_batch_fake + cdx_merkle_root_host",
+                                     "note": "includes generating the reference's fake data on the device (sequential per cell)"},
+            "batch_1000x4MiB": {"GB_per_s": n_small * small_bytes / t_b / 1e9, "ms": 1e3 * t_b, "one_by_one_GB_per_s": n_small * small_bytes / t_s / 1e9,
+                                "one_by_one_ms_extrapolated_from_100": 1e3 * t_s, "api": "cdx_slots_commit_batch_dev", "roots_equal_one_by_one": True,
+                                "timing": "wall clock around the call incl. the read-back of 1000 roots; data resident"},
+        }
+        del d_many
+        torch.cuda.empty_cache()
+        return out
+
+    # ---- BASELINE configs[3]: ONE 100 GiB slot split over the ranks (strong scaling) ----
+    n_total = (100 << 30) // BLOCK
+    T, ranges = capi.plan_block_ranges(n_total, world)
+    first, count = ranges[rank]
+    d = torch.empty(max(count, 1) * BLOCK, dtype=torch.uint8, device="cuda")
+    ctx.fill_synthetic_dev(SEED, first * (BLOCK // 8), count * BLOCK, d.data_ptr())
+    torch.cuda.synchronize()
+
+    def commit_100g():
+        sh = ctx.slot_commit_sharded_dev(comm, d.data_ptr(), count * BLOCK, CELL, BLOCK, first, n_total, T)
+        r = sh.root
+        sh.free()
+        return r
+    commit_100g()
+    ev_s, wall_s, root100 = timed(commit_100g, 2)
+    gbs = n_total * BLOCK * 2 / ev_s / 1e9
+    assert root100 == KNOWN_100GIB_ROOT, "100 GiB sharded root differs from the known single-GPU root"
+    out["config4_strong"] = {"workload": f"single 100 GiB synthetic slot ({n_total} blocks) split over {world} GPUs, exchange level {T}",
+                             "ms_per_step": 1e3 * ev_s / 2, "GB_per_s": gbs, "per_gpu_GB_per_s": gbs / world,
+                             "efficiency_vs_weak_per_gpu_rate": (gbs / world) / (weak_value / world), "slot_root": hex(root100),
+                             "root_equals_known_single_gpu_root": True, "steps": 2, "warmup": 1, "api": "cdx_slot_commit_sharded_dev + cdx_slot_root",
+                             "timing": "CUDA events on the library stream, barrier + synchronize on both sides, max over ranks"}
+    del d
+    torch.cuda.empty_cache()
+
+    # ---- sharded == whole: rank 0 commits the whole N x 10 GiB slot of the headline alone (tiled generation, no slot-sized buffer) ----
+    weak_bytes = int(args.slot_gib * (1 << 30)) // BLOCK * BLOCK * world
+    whole_root, t_whole = None, None
+    if rank == 0 and args.total_gib <= 0:
+        t0 = time.perf_counter()
+        with ctx.dataset_commit(None, [(capi.SRC_SYNTHETIC, SEED, weak_bytes)]) as ds1:
+            whole_root = ds1.slot_roots[0]
+        t_whole = time.perf_counter() - t0
+    barrier()
+    if rank == 0 and whole_root is not None:
+        out["sharded_root_check"] = {"whole_slot_bytes": weak_bytes, "whole_slot_root_one_gpu": hex(whole_root), "one_gpu_s": t_whole,
+                                     "api": "cdx_dataset_commit (one synthetic slot, one GPU, tiled generation)"}   # compared with the headline root by the caller
+
+    # ---- BASELINE configs[4]: dataset of 250 slots, mixed sizes, non-power-of-two count ----
+    if args.config5 == "on" or (args.config5 == "auto" and world == 8):
+        scale = args.config5_scale
+        blocks = dataset.draw_slot_blocks(args.config5_slots, scale * (1 << 30), scale * (100 << 30), 12345, pow2_slot=3, pow2_blocks=1 << 15)
+        descs = dataset.synthetic_descs(blocks, 12345)
+        barrier()
+        t0 = time.perf_counter()
+        ds = ctx.dataset_commit(comm, descs, keep_slot=3)
+        barrier()
+        t_commit = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        idx, paths, leaves = ds.prove(1234567, 100, 32)
+        t_prove = time.perf_counter() - t1
+        stats = ds.stats
+        tt = torch.tensor([t_commit, t_prove, float(stats["bytes_local"])], dtype=torch.float64, device="cuda")
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mn = tt.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        total_b = sum(blocks) * BLOCK
+        ok = True
+        # two-stage check of every sampled path on the GPU: block level, then slot level (Slot.hs:189-217)
+        if rank == 0:
+            blk = ctx.reconstruct_roots(leaves, [ci % 32 for ci in idx], 32, paths, depth=5)
+            top = ctx.reconstruct_roots(blk, [ci // 32 for ci in idx], blocks[3], [p[5:] for p in paths], depth=15)
+            ok = all(t == ds.slot_roots[3] for t in top)
+        out["config5"] = {"workload": f"dataset of {len(blocks)} synthetic slots, {scale:g}-{100 * scale:g} GiB log-uniform (seed 12345), slot 3 forced to 2 GiB and sampled",
+                          "bytes": total_b, "commit_s": float(mx[0]), "GB_per_s": total_b / float(mx[0]) / 1e9, "prove_100_samples_ms": 1e3 * float(mx[1]),
+                          "dataset_root": hex(ds.root), "slot_proof_depth": 8, "all_100_paths_reconstruct_slot_root": bool(ok),
+                          "per_rank_bytes_max_over_min": float(mx[2]) / max(float(mn[2]), 1.0), "rank0_stats": stats,
+                          "api": "cdx_dataset_commit + cdx_dataset_prove (LPT packing, batching, sharding, root exchange inside the library)",
+                          "timing": "wall clock, barrier on both sides, max over ranks; synthetic bytes generated on the device inside the timed region"}
+        ds.free()
+    return out
 
 
 if __name__ == "__main__":

@@ -62,7 +62,102 @@ SYMBOLS = {
     "cdx_fake_cells_dev": (_int, [_vp, _u64, _u64, _sz, _sz, _vp, _vp]),
     "cdx_fill_synthetic_dev": (_int, [_vp, _u64, _u64, _sz, _vp, _vp]),
     "cdx_probe_imad_rate": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cdx_merkle_root_bytes_host": (_int, [_vp, _vp, _sz, _vp]),
+    "cdx_slots_commit_batch_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp]),
+    "cdx_slots_commit_batch_host": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "cdx_slots_commit_batch_fake": (_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp]),
+    "cdx_comm_unique_id": (_int, [_vp]),
+    "cdx_comm_init_rank": (_int, [_vp, _int, _int, _vp, _pp]),
+    "cdx_comm_destroy": (None, [_vp]),
+    "cdx_comm_rank": (_int, [_vp]),
+    "cdx_comm_size": (_int, [_vp]),
+    "cdx_comm_barrier": (_int, [_vp]),
+    "cdx_plan_block_ranges": (_int, [_u64, _int, C.POINTER(_int), C.POINTER(_u64), C.POINTER(_u64)]),
+    "cdx_block_ranges_top_level": (_int, [_u64, _int, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_int)]),
+    "cdx_slot_commit_sharded_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _u64, _u64, _int, _vp, _pp]),
+    "cdx_slot_commit_sharded_host": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _u64, _u64, _int, _pp]),
+    "cdx_slot_exchange_top": (_int, [_vp, _vp]),
+    "cdx_slot_cell_paths_sharded": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
+    "cdx_slot_prove_batch_sharded": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp]),
+    "cdx_dataset_commit": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, C.c_int64, _pp]),
+    "cdx_dataset_free": (None, [_vp]),
+    "cdx_dataset_root": (_int, [_vp, _vp]),
+    "cdx_dataset_slot_roots": (_int, [_vp, _vp]),
+    "cdx_dataset_slot_proof": (_int, [_vp, _u64, _sz, _vp]),
+    "cdx_dataset_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "cdx_dataset_kept_slot": (_vp, [_vp]),
+    "cdx_dataset_prove": (_int, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
+    "cdx_group_create": (_int, [C.POINTER(_int), _int, _pp]),
+    "cdx_group_destroy": (None, [_vp]),
+    "cdx_group_size": (_int, [_vp]),
+    "cdx_group_ctx": (_vp, [_vp, _int]),
+    "cdx_group_comm": (_vp, [_vp, _int]),
+    "cdx_group_last_error": (C.c_char_p, [_vp]),
+    "cdx_group_slot_commit_host": (_int, [_vp, _vp, _sz, _sz, _sz, _pp]),
+    "cdx_group_slot_cell_paths": (_int, [_vp, _pp, _vp, _sz, _sz, _vp, _vp]),
+    "cdx_group_slots_free": (None, [_vp, _pp]),
+    "cdx_group_dataset_commit": (_int, [_vp, _vp, _sz, _sz, _sz, C.c_int64, _pp]),
+    "cdx_group_dataset_prove": (_int, [_vp, _pp, _vp, _sz, _sz, _vp, _vp, _vp]),
+    "cdx_group_datasets_free": (None, [_vp, _pp]),
 }
+
+COMM_ID_BYTES = 128
+SRC_FAKE, SRC_SYNTHETIC, SRC_FILE, SRC_HOST = 0, 1, 2, 3
+
+
+class SlotDesc(C.Structure):
+    """cdx_slot_desc: one slot of a dataset"""
+    _fields_ = [("kind", C.c_uint32), ("reserved", C.c_uint32), ("seed", C.c_uint64), ("path", C.c_char_p), ("host", C.c_void_p),
+                ("n_bytes", C.c_uint64)]
+
+
+def make_descs(descs):
+    """[(kind, seed | path | address, n_bytes)] -> (ctypes array, keep-alive list)"""
+    arr = (SlotDesc * len(descs))()
+    keep = []
+    for i, (kind, what, n_bytes) in enumerate(descs):
+        arr[i].kind, arr[i].n_bytes = kind, n_bytes
+        if kind in (SRC_FAKE, SRC_SYNTHETIC):
+            arr[i].seed = int(what) & (2**64 - 1)
+        elif kind == SRC_FILE:
+            b = os.fsencode(what)
+            keep.append(b)
+            arr[i].path = b
+        else:
+            keep.append(what)
+            arr[i].host = _addr(what)
+    return arr, keep
+
+
+def plan_block_ranges(n_total_blocks: int, n_ranks: int):
+    """cdx_plan_block_ranges -> (top_level, [(first_block, n_blocks)] per rank)"""
+    lib = load_library()
+    t = C.c_int()
+    first, count = (C.c_uint64 * n_ranks)(), (C.c_uint64 * n_ranks)()
+    rc = lib.cdx_plan_block_ranges(n_total_blocks, n_ranks, C.byref(t), first, count)
+    if rc != CDX_OK:
+        raise CodexCommitError(rc, "cdx_plan_block_ranges")
+    return t.value, [(int(first[r]), int(count[r])) for r in range(n_ranks)]
+
+
+def block_ranges_top_level(n_total_blocks: int, ranges) -> int:
+    lib = load_library()
+    n = len(ranges)
+    first, count = (C.c_uint64 * n)(*[r[0] for r in ranges]), (C.c_uint64 * n)(*[r[1] for r in ranges])
+    t = C.c_int()
+    rc = lib.cdx_block_ranges_top_level(n_total_blocks, n, first, count, C.byref(t))
+    if rc != CDX_OK:
+        raise CodexCommitError(rc, "cdx_block_ranges_top_level: ranges must be contiguous and cover the slot")
+    return t.value
+
+
+def comm_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib.cdx_comm_unique_id(buf)
+    if rc != CDX_OK:
+        raise CodexCommitError(rc, "cdx_comm_unique_id: libnccl.so.2 could not be loaded")
+    return buf.raw
 
 _lib = None
 
@@ -223,6 +318,62 @@ class Context:
         bl = pack(leaves)
         self._chk(self.lib.cdx_merkle_root_host(self.h, _addr(bl) if n else None, n, out))
         return b2f(out.raw)
+
+    def merkle_root_bytes(self, data: bytes) -> int:
+        """Merkle.digest(openArray[byte]) -- testvectors.nim:60-66"""
+        out = C.create_string_buffer(32)
+        d = bytes(data)
+        self._chk(self.lib.cdx_merkle_root_bytes_host(self.h, _addr(d) if d else None, len(d), out))
+        return b2f(out.raw)
+
+    # ---- many small slots ----
+    def slots_commit_batch_host(self, data, slot_bytes: Sequence[int], cell_size: int = 2048, block_size: int = 65536) -> List[int]:
+        n = len(slot_bytes)
+        sb = (C.c_uint64 * max(n, 1))(*slot_bytes)
+        out = C.create_string_buffer(32 * n if n else 1)
+        self._chk(self.lib.cdx_slots_commit_batch_host(self.h, _addr(data), sb, n, cell_size, block_size, out))
+        return unpack(out.raw[:32 * n])
+
+    def slots_commit_batch_dev(self, d_data: int, slot_bytes: Sequence[int], cell_size: int = 2048, block_size: int = 65536, stream: int = 0) -> List[int]:
+        n = len(slot_bytes)
+        sb = (C.c_uint64 * max(n, 1))(*slot_bytes)
+        out = C.create_string_buffer(32 * n if n else 1)
+        self._chk(self.lib.cdx_slots_commit_batch_dev(self.h, d_data, sb, n, cell_size, block_size, stream, out))
+        return unpack(out.raw[:32 * n])
+
+    def slots_commit_batch_fake(self, seeds: Sequence[int], n_cells: int, cell_size: int = 2048, block_size: int = 65536) -> List[int]:
+        n = len(seeds)
+        sd = (C.c_uint64 * max(n, 1))(*[x & (2**64 - 1) for x in seeds])
+        out = C.create_string_buffer(32 * n if n else 1)
+        self._chk(self.lib.cdx_slots_commit_batch_fake(self.h, sd, n, n_cells, cell_size, block_size, out))
+        return unpack(out.raw[:32 * n])
+
+    # ---- several GPUs ----
+    def comm_init(self, n_ranks: int, rank: int, unique_id: Optional[bytes]) -> "Comm":
+        h = C.c_void_p()
+        self._chk(self.lib.cdx_comm_init_rank(self.h, n_ranks, rank, unique_id, C.byref(h)))
+        return Comm(self, h)
+
+    def slot_commit_sharded_dev(self, comm: "Comm", d_data: int, n_local_bytes: int, cell_size: int, block_size: int, first_block: int,
+                                n_total_blocks: int, top_level: int, stream: int = 0) -> "Slot":
+        h = C.c_void_p()
+        self._chk(self.lib.cdx_slot_commit_sharded_dev(self.h, comm.h if comm else None, d_data, n_local_bytes, cell_size, block_size, first_block,
+                                                       n_total_blocks, top_level, stream, C.byref(h)))
+        return Slot(self, h)
+
+    def slot_commit_sharded_host(self, comm: "Comm", data, n_local_bytes: int, cell_size: int, block_size: int, first_block: int,
+                                 n_total_blocks: int, top_level: int) -> "Slot":
+        h = C.c_void_p()
+        self._chk(self.lib.cdx_slot_commit_sharded_host(self.h, comm.h if comm else None, _addr(data) if n_local_bytes else None, n_local_bytes,
+                                                        cell_size, block_size, first_block, n_total_blocks, top_level, C.byref(h)))
+        return Slot(self, h)
+
+    def dataset_commit(self, comm: Optional["Comm"], descs, cell_size: int = 2048, block_size: int = 65536, keep_slot: int = -1) -> "Dataset":
+        """descs: [(kind, seed | path | buffer, n_bytes)]"""
+        arr, keep = make_descs(descs)
+        h = C.c_void_p()
+        self._chk(self.lib.cdx_dataset_commit(self.h, comm.h if comm else None, arr, len(descs), cell_size, block_size, keep_slot, C.byref(h)))
+        return Dataset(self, h, len(descs))
 
     # ---- slots ----
     def slot_commit_host(self, data, cell_size: int = 2048, block_size: int = 65536, n_bytes: Optional[int] = None) -> "Slot":
@@ -393,3 +544,108 @@ class Slot:
 
     def set_top_dev(self, d_nodes: int, n_nodes: int, stream: int = 0):
         self.ctx._chk(self.ctx.lib.cdx_slot_set_top_dev(self.h, d_nodes, n_nodes, stream))
+
+    def exchange_top(self, comm: Optional["Comm"]):
+        self.ctx._chk(self.ctx.lib.cdx_slot_exchange_top(self.h, comm.h if comm else None))
+
+    def cell_paths_sharded(self, comm: Optional["Comm"], cell_indices: Sequence[int], max_depth: int):
+        """collective: every rank receives (paths[n][max_depth], leaves[n])"""
+        n = len(cell_indices)
+        idx = (C.c_uint64 * max(n, 1))(*cell_indices)
+        out = C.create_string_buffer(32 * n * max_depth if n else 1)
+        leaf = C.create_string_buffer(32 * n if n else 1)
+        self.ctx._chk(self.ctx.lib.cdx_slot_cell_paths_sharded(self.h, comm.h if comm else None, C.addressof(idx), n, max_depth, C.addressof(out),
+                                                               C.addressof(leaf)))
+        flat = unpack(out.raw[:32 * n * max_depth])
+        return [flat[i * max_depth:(i + 1) * max_depth] for i in range(n)], unpack(leaf.raw[:32 * n])
+
+    def prove_batch_sharded(self, comm: Optional["Comm"], entropies: Sequence[int], n_samples: int, max_depth: int):
+        k = len(entropies)
+        total = k * n_samples
+        ent = b"".join(f2b(e) for e in entropies)
+        idx = (C.c_uint64 * max(total, 1))()
+        out = C.create_string_buffer(32 * total * max_depth if total else 1)
+        leaf = C.create_string_buffer(32 * total if total else 1)
+        self.ctx._chk(self.ctx.lib.cdx_slot_prove_batch_sharded(self.h, comm.h if comm else None, _addr(ent), k, n_samples, max_depth, C.addressof(idx),
+                                                                C.addressof(out), C.addressof(leaf)))
+        flat = unpack(out.raw[:32 * total * max_depth])
+        leaves = unpack(leaf.raw[:32 * total])
+        ii = list(idx)[:total]
+        paths = [flat[i * max_depth:(i + 1) * max_depth] for i in range(total)]
+        return ([ii[j * n_samples:(j + 1) * n_samples] for j in range(k)],
+                [paths[j * n_samples:(j + 1) * n_samples] for j in range(k)],
+                [leaves[j * n_samples:(j + 1) * n_samples] for j in range(k)])
+
+
+class Comm:
+    """One rank of a communicator (cdx_comm): NCCL inside the library, nothing for a single rank."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    @property
+    def rank(self) -> int:
+        return self.ctx.lib.cdx_comm_rank(self.h)
+
+    @property
+    def size(self) -> int:
+        return self.ctx.lib.cdx_comm_size(self.h)
+
+    def barrier(self):
+        self.ctx._chk(self.ctx.lib.cdx_comm_barrier(self.h))
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.cdx_comm_destroy(self.h)
+            self.h = None
+
+
+class Dataset:
+    """A committed dataset (cdx_dataset): slot roots, dataset tree, optionally one retained slot."""
+
+    def __init__(self, ctx: Context, h, n_slots: int):
+        self.ctx, self.h, self.n_slots = ctx, h, n_slots
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.cdx_dataset_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.free()
+
+    @property
+    def root(self) -> int:
+        out = C.create_string_buffer(32)
+        self.ctx._chk(self.ctx.lib.cdx_dataset_root(self.h, out))
+        return b2f(out.raw)
+
+    @property
+    def slot_roots(self) -> List[int]:
+        out = C.create_string_buffer(32 * self.n_slots)
+        self.ctx._chk(self.ctx.lib.cdx_dataset_slot_roots(self.h, out))
+        return unpack(out.raw)
+
+    def slot_proof(self, slot_index: int, max_log2_nslots: int) -> List[int]:
+        out = C.create_string_buffer(32 * max_log2_nslots if max_log2_nslots else 1)
+        self.ctx._chk(self.ctx.lib.cdx_dataset_slot_proof(self.h, slot_index, max_log2_nslots, out))
+        return unpack(out.raw[:32 * max_log2_nslots])
+
+    @property
+    def stats(self):
+        b, w, ba, sh = C.c_uint64(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.ctx._chk(self.ctx.lib.cdx_dataset_stats(self.h, C.byref(b), C.byref(w), C.byref(ba), C.byref(sh)))
+        return {"bytes_local": b.value, "whole": w.value, "batched": ba.value, "sharded": sh.value}
+
+    def prove(self, entropy: int, n_samples: int, max_depth: int):
+        """-> (indices[n], paths[n][max_depth], leaves[n]); collective if the dataset has a communicator"""
+        idx = (C.c_uint64 * max(n_samples, 1))()
+        out = C.create_string_buffer(32 * n_samples * max_depth if n_samples else 1)
+        leaf = C.create_string_buffer(32 * n_samples if n_samples else 1)
+        be = f2b(entropy)
+        self.ctx._chk(self.ctx.lib.cdx_dataset_prove(self.h, _addr(be), n_samples, max_depth, idx, out, leaf))
+        flat = unpack(out.raw[:32 * n_samples * max_depth])
+        return (list(idx)[:n_samples], [flat[i * max_depth:(i + 1) * max_depth] for i in range(n_samples)], unpack(leaf.raw[:32 * n_samples]))

@@ -610,114 +610,68 @@ static int ensure_stage(cdx_ctx* ctx, size_t bytes) {
   return CDX_OK;
 }
 
-// Host-resident slot (or block range of one): the bytes stream through two device tiles; the copy of tile t+1 (copy
-// stream) overlaps the cell sponge of tile t (compute stream).  Only hashes stay resident.
+// ---- cell-hash pipelines: slot bytes that are not resident in HBM -------------------------------------------------
+// Each of the three streams its source through two device tiles and leaves the cell hashes in d_hashes.  They queue work
+// on ctx->stream / ctx->stream2 / ctx->copy_stream and return with ctx->stream ordered after all of it (no host sync);
+// the caller continues on ctx->stream.
 typedef std::function<void(uint8_t* dst, uint64_t offset, size_t len)> ChunkFill;
-static int commit_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block, uint64_t n_total_blocks,
-                         int top_level, bool whole_slot, const ChunkFill& fill, cdx_slot** out);
 
-static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block,
-                             uint64_t n_total_blocks, int top_level, bool whole_slot, cdx_slot** out) {
-  if (!ctx || !data || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
-  *out = nullptr;
-  int rc = check_shape(ctx, n_bytes, cell_size, block_size);
-  if (rc) return rc;
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if (n_bytes >= ((size_t)256 << 20) && !ctx->no_bounce) {
-    // Pageable memory (an ordinary malloc / Nim seq) is copied by the driver through one staging thread at ~11 GB/s,
-    // below the sponge rate; several host threads copying into our own pinned chunks keep up with it.
-    cudaPointerAttributes attr;
-    const cudaError_t e = cudaPointerGetAttributes(&attr, data);
-    if (e != cudaSuccess) cudaGetLastError();
-    if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) {
-      ChunkFill fill = [data](uint8_t* dst, uint64_t off, size_t len) { memcpy(dst, data + off, len); };
-      return commit_staged(ctx, n_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, whole_slot, fill, out);
-    }
-  }
+static void drain_streams(cdx_ctx* ctx) {
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->stream2);
+  cudaStreamSynchronize(ctx->stream);
+}
+
+// Pinned (or otherwise DMA-able) host memory: the copy of tile t+1 (copy stream) overlaps the cell sponge of tile t.
+static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, uint8_t* d_hashes) {
   const size_t n_blocks = n_bytes / block_size;
-  if (whole_slot) n_total_blocks = n_blocks;
   // Tile = 256 MiB: 131 072 cells of 2 KiB, about one full wave of the cell-sponge kernel on 148 SMs (the resident
   // CTAs per SM are set by CDX_TMA_MIN_CTAS in kernels.cuh); smaller tiles leave SMs idle, larger ones only add exposed
-  // first-copy latency.
-  // Slots below 1 GiB are cut in four so that the copy still overlaps.
+  // first-copy latency.  Slots below 1 GiB are cut in four so that the copy still overlaps.
   size_t tile_bytes_target = (size_t)256 << 20;
   if (n_bytes < ((size_t)1 << 30)) tile_bytes_target = n_bytes / 4 > ((size_t)16 << 20) ? n_bytes / 4 : ((size_t)16 << 20);
   size_t tile_blocks = tile_bytes_target / block_size;
   if (tile_blocks == 0) tile_blocks = 1;
   if (tile_blocks > n_blocks) tile_blocks = n_blocks;
-  const size_t tile_bytes = tile_blocks * block_size;
-  rc = ensure_stage(ctx, tile_bytes);
-  if (rc) return rc;
-  cdx_slot* s = nullptr;
-  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, first_block, n_total_blocks, top_level, ctx->stream, &s);
+  int rc = ensure_stage(ctx, tile_blocks * block_size);
   if (rc) return rc;
   const size_t cpb = block_size / cell_size;
-  auto body = [&]() -> int {
-    // tile t lives in staging buffer t&1 and is hashed on compute stream t&1, so the cell kernels of consecutive
-    // tiles overlap at the seams (the tail of one fills up with the head of the next) while each buffer is still
-    // reused strictly in order: copy(t) waits for hash(t-2), hash(t) waits for copy(t).
-    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));              // the slot's buffers were allocated on stream
-    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
-    size_t done = 0;
-    const size_t first_tile = tile_blocks / 8 ? tile_blocks / 8 : 1;
-    const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
-    for (int t = 0; done < n_blocks; ++t) {
-      const int b = t & 1;
-      cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
-      // the copy of tile 0 is the only one nothing overlaps: keep it short (1/8 tile), then realign with tile 1
-      size_t want = tile_blocks;
-      if (ramp && t == 0) want = first_tile;
-      else if (ramp && t == 1) want = tile_blocks - first_tile;
-      const size_t nb = n_blocks - done < want ? n_blocks - done : want;
-      if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
-      CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, ctx->copy_stream));
-      CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-      CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
-      int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, s->forest[0] + 32 * done * cpb, cs);
-      if (hr) return hr;
-      CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], cs));
-      done += nb;
-    }
-    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));             // trees run on stream after both tile streams
-    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    int r = build_local_trees(s);
-    if (r) return r;
-    if (whole_slot) {
-      r = build_top(s, s->low[0], true);
-      if (r) return r;
-    }
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return CDX_OK;
-  };
-  rc = body();
-  if (rc) {
-    cudaStreamSynchronize(ctx->copy_stream);
-    cudaStreamSynchronize(ctx->stream2);
-    cudaStreamSynchronize(ctx->stream);
-    cdx_slot_free(s);
-    return rc;
+  // tile t lives in staging buffer t&1 and is hashed on compute stream t&1, so the cell kernels of consecutive
+  // tiles overlap at the seams (the tail of one fills up with the head of the next) while each buffer is still
+  // reused strictly in order: copy(t) waits for hash(t-2), hash(t) waits for copy(t).
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));              // the hash buffer was allocated on stream
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));  // and the staging tiles may still be read by earlier work on it
+  size_t done = 0;
+  const size_t first_tile = tile_blocks / 8 ? tile_blocks / 8 : 1;
+  const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
+  for (int t = 0; done < n_blocks; ++t) {
+    const int b = t & 1;
+    cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
+    // the copy of tile 0 is the only one nothing overlaps: keep it short (1/8 tile), then realign with tile 1
+    size_t want = tile_blocks;
+    if (ramp && t == 0) want = first_tile;
+    else if (ramp && t == 1) want = tile_blocks - first_tile;
+    const size_t nb = n_blocks - done < want ? n_blocks - done : want;
+    if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
+    int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, d_hashes + 32 * done * cpb, cs);
+    if (hr) return hr;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], cs));
+    done += nb;
   }
-  *out = s;
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));             // the caller's trees run on stream after both tile streams
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   return CDX_OK;
-}
-
-extern "C" int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
-  return commit_host_range(ctx, data, n_bytes, cell_size, block_size, 0, 0, 0, true, out);
-}
-
-extern "C" int cdx_slot_commit_range_host(cdx_ctx* ctx, const uint8_t* data, size_t n_local_bytes, size_t cell_size, size_t block_size,
-                                          uint64_t first_block, uint64_t n_total_blocks, int top_level, cdx_slot** out) {
-  return commit_host_range(ctx, data, n_local_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, false, out);
 }
 
 // Slot bytes that are not directly DMA-able (a file, or pageable host memory -- what a Nim seq[byte] is).  Three
 // overlapped stages: host threads fill one of two pinned chunks through `fill(dst, offset, len)`, H2D of that chunk
 // into the current device tile (copy stream), cell sponge per finished tile (alternating compute streams).
-static int commit_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block, uint64_t n_total_blocks,
-                         int top_level, bool whole_slot, const ChunkFill& fill, cdx_slot** out) {
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
+static int hash_cells_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t block_size, const ChunkFill& fill, uint8_t* d_hashes) {
   const size_t n_blocks = n_bytes / block_size;
-  if (whole_slot) n_total_blocks = n_blocks;
   const size_t chunk_bytes_target = (size_t)64 << 20;                       // pinned chunk
   size_t chunk_blocks = chunk_bytes_target / block_size ? chunk_bytes_target / block_size : 1;
   size_t tile_blocks = 4 * chunk_blocks;                                    // device tile = 4 chunks = 256 MiB (one sponge wave)
@@ -737,9 +691,6 @@ static int commit_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t 
   }
   int rc = ensure_stage(ctx, tile_bytes);
   if (rc) return rc;
-  cdx_slot* s = nullptr;
-  rc = slot_alloc(ctx, n_blocks, cell_size, block_size, first_block, n_total_blocks, top_level, ctx->stream, &s);
-  if (rc) return rc;
   const size_t cpb = block_size / cell_size;
   unsigned hw = std::thread::hardware_concurrency();
   const unsigned n_thr = hw >= 16 ? 8 : (hw >= 8 ? 4 : 2);
@@ -751,57 +702,167 @@ static int commit_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t 
     }
     for (auto& t : thr) t.join();
   };
-  auto body = [&]() -> int {
-    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));
-    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
-    size_t done_blocks = 0, chunk_no = 0;
-    const bool ramp = n_blocks > tile_blocks && tile_blocks > chunk_blocks;
-    for (int t = 0; done_blocks < n_blocks; ++t) {
-      const int b = t & 1;
-      cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
-      // tile 0 is one chunk, tile 1 the other three: the sponge starts after one chunk has been filled and copied, not four
-      size_t want = tile_blocks;
-      if (ramp && t == 0) want = chunk_blocks;
-      else if (ramp && t == 1) want = tile_blocks - chunk_blocks;
-      const size_t nb = n_blocks - done_blocks < want ? n_blocks - done_blocks : want;
-      if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));   // device tile b free again
-      for (size_t cb = 0; cb < nb; cb += chunk_blocks, ++chunk_no) {
-        const int pb = (int)(chunk_no & 1);
-        const size_t cnb = nb - cb < chunk_blocks ? nb - cb : chunk_blocks;
-        if (chunk_no >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_h2d[pb]));                  // pinned chunk pb drained
-        fill_chunk_parallel((uint8_t*)ctx->h_pinned[pb], (uint64_t)(done_blocks + cb) * block_size, cnb * block_size);
-        CU_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->d_stage[b] + cb * block_size, ctx->h_pinned[pb], cnb * block_size, cudaMemcpyHostToDevice,
-                                    ctx->copy_stream));
-        CU_TRY(ctx, cudaEventRecord(ctx->ev_h2d[pb], ctx->copy_stream));
-      }
-      CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-      CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
-      int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, s->forest[0] + 32 * done_blocks * cpb, cs);
-      if (hr) return hr;
-      CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], cs));
-      done_blocks += nb;
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));
+  size_t done_blocks = 0, chunk_no = 0;
+  const bool ramp = n_blocks > tile_blocks && tile_blocks > chunk_blocks;
+  for (int t = 0; done_blocks < n_blocks; ++t) {
+    const int b = t & 1;
+    cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
+    // tile 0 is one chunk, tile 1 the other three: the sponge starts after one chunk has been filled and copied, not four
+    size_t want = tile_blocks;
+    if (ramp && t == 0) want = chunk_blocks;
+    else if (ramp && t == 1) want = tile_blocks - chunk_blocks;
+    const size_t nb = n_blocks - done_blocks < want ? n_blocks - done_blocks : want;
+    if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));   // device tile b free again
+    for (size_t cb = 0; cb < nb; cb += chunk_blocks, ++chunk_no) {
+      const int pb = (int)(chunk_no & 1);
+      const size_t cnb = nb - cb < chunk_blocks ? nb - cb : chunk_blocks;
+      if (chunk_no >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_h2d[pb]));                  // pinned chunk pb drained
+      fill_chunk_parallel((uint8_t*)ctx->h_pinned[pb], (uint64_t)(done_blocks + cb) * block_size, cnb * block_size);
+      CU_TRY(ctx, cudaMemcpyAsync((uint8_t*)ctx->d_stage[b] + cb * block_size, ctx->h_pinned[pb], cnb * block_size, cudaMemcpyHostToDevice,
+                                  ctx->copy_stream));
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_h2d[pb], ctx->copy_stream));
     }
-    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
-    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    int r = build_local_trees(s);
-    if (r) return r;
-    if (whole_slot) {
-      r = build_top(s, s->low[0], true);
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
+    int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, d_hashes + 32 * done_blocks * cpb, cs);
+    if (hr) return hr;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_consumed[b], cs));
+    done_blocks += nb;
+  }
+  // the pinned chunks are reused by the next call: their last copies must have left the host
+  CU_TRY(ctx, cudaEventSynchronize(ctx->ev_h2d[0]));
+  if (chunk_no >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_h2d[1]));
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  return CDX_OK;
+}
+
+// Host memory of either kind.  Pageable memory (an ordinary malloc / Nim seq) is copied by the driver through one staging
+// thread at ~11 GB/s, below the sponge rate; several host threads copying into our own pinned chunks keep up with it.
+static int hash_cells_host(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, uint8_t* d_hashes) {
+  if (n_bytes >= ((size_t)256 << 20) && !ctx->no_bounce) {
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, data);
+    if (e != cudaSuccess) cudaGetLastError();
+    if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) {
+      ChunkFill fill = [data](uint8_t* dst, uint64_t off, size_t len) { memcpy(dst, data + off, len); };
+      return hash_cells_staged(ctx, n_bytes, cell_size, block_size, fill, d_hashes);
+    }
+  }
+  return hash_cells_pinned(ctx, data, n_bytes, cell_size, block_size, d_hashes);
+}
+
+// Generated slot bytes (the reference's fake data or the benchmark's counter-based bytes): the generator kernel writes a
+// device tile, the sponge reads it on the same stream; two tiles on two streams.  Nothing crosses PCIe and no slot-sized
+// buffer exists, so a 100 GiB slot costs 512 MiB of staging.  first_byte is the offset of this range inside its slot.
+static int launch_fake_cells(cdx_ctx* ctx, uint64_t seed, uint64_t first_cell, size_t n_cells, size_t cell_size, void* d_out, cudaStream_t st);
+static int launch_fill_synthetic(cdx_ctx* ctx, uint64_t seed, uint64_t first_word, size_t n_bytes, void* d_out, cudaStream_t st);
+static int generate_bytes(cdx_ctx* ctx, uint32_t kind, uint64_t seed, uint64_t first_byte, size_t n_bytes, size_t cell_size, void* d_out, cudaStream_t st) {
+  if (kind == CDX_SRC_FAKE) return launch_fake_cells(ctx, seed, first_byte / cell_size, n_bytes / cell_size, cell_size, d_out, st);
+  return launch_fill_synthetic(ctx, seed, first_byte / 8, n_bytes, d_out, st);
+}
+static int hash_cells_generated(cdx_ctx* ctx, uint32_t kind, uint64_t seed, uint64_t first_byte, size_t n_bytes, size_t cell_size, size_t block_size,
+                                uint8_t* d_hashes) {
+  const size_t n_blocks = n_bytes / block_size;
+  size_t tile_blocks = ((size_t)256 << 20) / block_size;
+  if (tile_blocks == 0) tile_blocks = 1;
+  if (tile_blocks > n_blocks) tile_blocks = n_blocks;
+  int rc = ensure_stage(ctx, tile_blocks * block_size);
+  if (rc) return rc;
+  const size_t cpb = block_size / cell_size;
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
+  size_t done = 0;
+  for (int t = 0; done < n_blocks; ++t) {
+    cudaStream_t cs = (t & 1) ? ctx->stream2 : ctx->stream;           // tile b is only ever touched on stream b: ordered by the stream
+    const size_t nb = n_blocks - done < tile_blocks ? n_blocks - done : tile_blocks;
+    rc = generate_bytes(ctx, kind, seed, first_byte + done * block_size, nb * block_size, cell_size, ctx->d_stage[t & 1], cs);
+    if (rc) return rc;
+    rc = launch_hash_cells(ctx, ctx->d_stage[t & 1], nb * cpb, cell_size, d_hashes + 32 * done * cpb, cs);
+    if (rc) return rc;
+    done += nb;
+  }
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  return CDX_OK;
+}
+
+// where the bytes of a slot (or of a block range of one) come from
+struct SlotSource {
+  uint32_t kind = CDX_SRC_HOST;
+  uint64_t seed = 0;
+  const uint8_t* host = nullptr;        // CDX_SRC_HOST: first byte of the RANGE
+  const ChunkFill* fill = nullptr;      // CDX_SRC_FILE: reads range-relative offsets
+  uint64_t first_byte = 0;              // generated kinds: offset of the range inside its slot
+};
+
+static int hash_cells_source(cdx_ctx* ctx, const SlotSource& src, size_t n_bytes, size_t cell_size, size_t block_size, uint8_t* d_hashes) {
+  switch (src.kind) {
+    case CDX_SRC_HOST: return hash_cells_host(ctx, src.host, n_bytes, cell_size, block_size, d_hashes);
+    case CDX_SRC_FILE: return hash_cells_staged(ctx, n_bytes, cell_size, block_size, *src.fill, d_hashes);
+    case CDX_SRC_FAKE:
+    case CDX_SRC_SYNTHETIC: return hash_cells_generated(ctx, src.kind, src.seed, src.first_byte, n_bytes, cell_size, block_size, d_hashes);
+    default: return fail(ctx, CDX_ERR_ARG, "unknown slot source kind %u", src.kind);
+  }
+}
+
+// A slot (whole_slot) or a block range of one, from any non-resident source: cell hashes through the matching pipeline,
+// then block trees and the local slot levels (and the top tree for a whole slot) on ctx->stream.  Returns synchronised.
+// n_bytes == 0 is an empty shard (sharded entry points only).
+static int commit_from_source(cdx_ctx* ctx, const SlotSource& src, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block,
+                              uint64_t n_total_blocks, int top_level, bool whole_slot, bool sync, cdx_slot** out) {
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n_blocks = n_bytes / block_size;
+  if (whole_slot) n_total_blocks = n_blocks;
+  cdx_slot* s = nullptr;
+  int rc = slot_alloc(ctx, n_blocks, cell_size, block_size, first_block, n_total_blocks, top_level, ctx->stream, &s, !whole_slot);
+  if (rc) return rc;
+  auto body = [&]() -> int {
+    if (n_blocks) {
+      int r = hash_cells_source(ctx, src, n_bytes, cell_size, block_size, s->forest[0]);
+      if (r) return r;
+      r = build_local_trees(s);
       if (r) return r;
     }
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (whole_slot) {
+      int r = build_top(s, s->low[0], true);
+      if (r) return r;
+    }
+    if (sync) CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CDX_OK;
   };
   rc = body();
   if (rc) {
-    cudaStreamSynchronize(ctx->copy_stream);
-    cudaStreamSynchronize(ctx->stream2);
-    cudaStreamSynchronize(ctx->stream);
+    drain_streams(ctx);
     cdx_slot_free(s);
     return rc;
   }
   *out = s;
   return CDX_OK;
+}
+
+static int commit_host_range(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block,
+                             uint64_t n_total_blocks, int top_level, bool whole_slot, cdx_slot** out) {
+  if (!ctx || !data || !out) return fail(ctx, CDX_ERR_ARG, "null pointer");
+  *out = nullptr;
+  int rc = check_shape(ctx, n_bytes, cell_size, block_size);
+  if (rc) return rc;
+  SlotSource src;
+  src.kind = CDX_SRC_HOST;
+  src.host = data;
+  return commit_from_source(ctx, src, n_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, whole_slot, true, out);
+}
+
+extern "C" int cdx_slot_commit_host(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
+  return commit_host_range(ctx, data, n_bytes, cell_size, block_size, 0, 0, 0, true, out);
+}
+
+extern "C" int cdx_slot_commit_range_host(cdx_ctx* ctx, const uint8_t* data, size_t n_local_bytes, size_t cell_size, size_t block_size,
+                                          uint64_t first_block, uint64_t n_total_blocks, int top_level, cdx_slot** out) {
+  return commit_host_range(ctx, data, n_local_bytes, cell_size, block_size, first_block, n_total_blocks, top_level, false, out);
 }
 
 extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t offset, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** out) {
@@ -829,7 +890,10 @@ extern "C" int cdx_slot_commit_file(cdx_ctx* ctx, const char* path, uint64_t off
     }
     if (pos < len) memset(dst + pos, 0, len - pos);
   };
-  rc = commit_staged(ctx, n_bytes, cell_size, block_size, 0, 0, 0, true, fill, out);
+  SlotSource src;
+  src.kind = CDX_SRC_FILE;
+  src.fill = &fill;
+  rc = commit_from_source(ctx, src, n_bytes, cell_size, block_size, 0, 0, 0, true, true, out);
   close(fd);
   if (rc == CDX_OK && io_errno.load() != 0) {
     cdx_slot_free(*out);
@@ -845,21 +909,10 @@ extern "C" int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells,
   if (cell_size == 0 || n_cells == 0 || n_cells > ((size_t)1 << 40) / cell_size) return fail(ctx, CDX_ERR_SIZE, "bad fake slot size");
   int rc = check_shape(ctx, n_cells * cell_size, cell_size, block_size);
   if (rc) return rc;
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  DevBuf d;
-  CU_TRY(ctx, d.alloc(n_cells * cell_size, ctx->stream));
-  rc = cdx_fake_cells_dev(ctx, seed, 0, n_cells, cell_size, d.p, ctx->stream);
-  if (rc) return rc;
-  cdx_slot* s = nullptr;
-  rc = cdx_slot_commit_dev(ctx, d.p, n_cells * cell_size, cell_size, block_size, ctx->stream, &s);
-  if (rc) return rc;
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);   // the data buffer dies with this scope
-  if (e != cudaSuccess) {
-    cdx_slot_free(s);
-    return fail(ctx, CDX_ERR_CUDA, "fake slot commit failed: %s", cudaGetErrorString(e));
-  }
-  *out = s;
-  return CDX_OK;
+  SlotSource src;
+  src.kind = CDX_SRC_FAKE;
+  src.seed = seed;
+  return commit_from_source(ctx, src, n_cells * cell_size, cell_size, block_size, 0, 0, 0, true, true, out);
 }
 
 // ---- persisted commitments ------------------------------------------------------------------------------------
@@ -1064,35 +1117,13 @@ static void make_path_plan(const cdx_slot* s, PathPlan& plan) {
   plan.cells_per_block_log2 = s->cpb_log2;
 }
 
+struct cdx_comm;
+static int prove_core(const cdx_slot* s, cdx_comm* comm, const uint8_t* entropies, size_t n_challenges, size_t n_samples, const uint64_t* cells,
+                      size_t max_depth, bool contribute_indices, uint64_t* indices_out, uint8_t* paths_out, uint8_t* leaves_out);   // capi_multi.cuh
+
 extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indices, size_t n_samples, size_t max_depth, uint8_t* out, uint8_t* leaf_out) {
   if (!s || !cell_indices || !out) return CDX_ERR_ARG;
-  cdx_ctx* ctx = s->ctx;
-  if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "no top tree yet");
-  if (n_samples == 0) return CDX_OK;
-  const uint64_t n_cells_total = s->n_total_blocks << s->cpb_log2;
-  if (max_depth < s->block_depth + s->slot_depth || max_depth > 64)
-    return fail(ctx, CDX_ERR_RANGE, "max_depth %zu < path length %u (padMerkleProof)", max_depth, s->block_depth + s->slot_depth);
-  if (n_samples > (1u << 20)) return fail(ctx, CDX_ERR_SIZE, "too many samples in one call");
-  for (size_t i = 0; i < n_samples; ++i)
-    if (cell_indices[i] >= n_cells_total) return fail(ctx, CDX_ERR_RANGE, "cell index %llu >= %llu", (unsigned long long)cell_indices[i], (unsigned long long)n_cells_total);
-  if (s->block_depth > 32 || s->slot_depth >= 40) return fail(ctx, CDX_ERR_RANGE, "tree too deep for the path plan");
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  PathPlan plan;
-  make_path_plan(s, plan);
-  DevBuf d_idx, d_out, d_leaf;
-  CU_TRY(ctx, d_idx.alloc(8 * n_samples, s->stream));
-  CU_TRY(ctx, d_out.alloc(32 * n_samples * max_depth, s->stream));
-  CU_TRY(ctx, d_leaf.alloc(32 * n_samples, s->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(d_idx.p, cell_indices, 8 * n_samples, cudaMemcpyHostToDevice, s->stream));
-  const size_t threads = n_samples * (max_depth + 1) * 2;
-  k_gather_paths<<<grid_for(threads, 256), 256, 0, s->stream>>>(plan, (const uint64_t*)d_idx.p, (uint32_t)n_samples, (uint32_t)max_depth,
-                                                               d_out.u8(), d_leaf.u8());
-  ctx->launches++;
-  CU_TRY(ctx, cudaGetLastError());
-  CU_TRY(ctx, cudaMemcpyAsync(out, d_out.p, 32 * n_samples * max_depth, cudaMemcpyDeviceToHost, s->stream));
-  if (leaf_out) CU_TRY(ctx, cudaMemcpyAsync(leaf_out, d_leaf.p, 32 * n_samples, cudaMemcpyDeviceToHost, s->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(s->stream));
-  return CDX_OK;
+  return prove_core(s, nullptr, nullptr, 0, n_samples, cell_indices, max_depth, true, nullptr, out, leaf_out);
 }
 
 // Proof-server call: many challenges against one retained commitment.  Per challenge the reference
@@ -1102,38 +1133,8 @@ extern "C" int cdx_slot_cell_paths(const cdx_slot* s, const uint64_t* cell_indic
 extern "C" int cdx_slot_prove_batch(const cdx_slot* s, const uint8_t* entropies, size_t n_challenges, size_t n_samples, size_t max_depth,
                                     uint64_t* indices_out, uint8_t* paths_out, uint8_t* leaves_out) {
   if (!s || !entropies || !indices_out || !paths_out) return CDX_ERR_ARG;
-  cdx_ctx* ctx = s->ctx;
-  if (!s->has_top) return fail(ctx, CDX_ERR_STATE, "no top tree yet");
-  const uint64_t n_cells_total = s->n_total_blocks << s->cpb_log2;
-  if (!is_pow2(n_cells_total)) return fail(ctx, CDX_ERR_NOT_POW2, "for this version, `numberOfCells` is assumed to be a power of two");
-  if (max_depth < s->block_depth + s->slot_depth || max_depth > 64)
-    return fail(ctx, CDX_ERR_RANGE, "max_depth %zu < path length %u (padMerkleProof)", max_depth, s->block_depth + s->slot_depth);
-  if (s->block_depth > 32 || s->slot_depth >= 40) return fail(ctx, CDX_ERR_RANGE, "tree too deep for the path plan");
-  if (n_challenges == 0 || n_samples == 0) return CDX_OK;
-  if (n_samples > 0xffffffffu || n_challenges > (1u << 20) || n_challenges * n_samples > (1u << 20))
-    return fail(ctx, CDX_ERR_SIZE, "too many (challenge, sample) pairs in one call");
-  const size_t total = n_challenges * n_samples;
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  PathPlan plan;
-  make_path_plan(s, plan);
-  DevBuf d_ent, d_idx, d_out, d_leaf;
-  CU_TRY(ctx, d_ent.alloc(32 * n_challenges, s->stream));
-  CU_TRY(ctx, d_idx.alloc(8 * total, s->stream));
-  CU_TRY(ctx, d_out.alloc(32 * total * max_depth, s->stream));
-  CU_TRY(ctx, d_leaf.alloc(32 * total, s->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(d_ent.p, entropies, 32 * n_challenges, cudaMemcpyHostToDevice, s->stream));
-  LAUNCH(ctx, k_cell_indices, total, s->stream, d_ent.u8(), (const uint8_t*)s->top[s->slot_depth], n_cells_total - 1, (uint32_t)n_samples, total,
-         (uint64_t*)d_idx.p);
-  const size_t threads = total * (max_depth + 1) * 2;
-  k_gather_paths<<<grid_for(threads, 256), 256, 0, s->stream>>>(plan, (const uint64_t*)d_idx.p, (uint32_t)total, (uint32_t)max_depth, d_out.u8(),
-                                                               d_leaf.u8());
-  ctx->launches++;
-  CU_TRY(ctx, cudaGetLastError());
-  CU_TRY(ctx, cudaMemcpyAsync(indices_out, d_idx.p, 8 * total, cudaMemcpyDeviceToHost, s->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(paths_out, d_out.p, 32 * total * max_depth, cudaMemcpyDeviceToHost, s->stream));
-  if (leaves_out) CU_TRY(ctx, cudaMemcpyAsync(leaves_out, d_leaf.p, 32 * total, cudaMemcpyDeviceToHost, s->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(s->stream));
-  return CDX_OK;
+  if (n_samples > 0xffffffffu) return fail(s->ctx, CDX_ERR_SIZE, "too many samples");
+  return prove_core(s, nullptr, entropies, n_challenges, n_samples, nullptr, max_depth, true, indices_out, paths_out, leaves_out);
 }
 
 extern "C" int cdx_reconstruct_roots_host(cdx_ctx* ctx, const uint8_t* leaves, const uint64_t* indices, uint64_t n_leaves, const uint8_t* paths,
@@ -1177,13 +1178,16 @@ extern "C" int cdx_cell_indices(cdx_ctx* ctx, const uint8_t entropy[32], const u
   return CDX_OK;
 }
 
+static int launch_fake_cells(cdx_ctx* ctx, uint64_t seed, uint64_t first_cell, size_t n_cells, size_t cell_size, void* d_out, cudaStream_t st) {
+  LAUNCH(ctx, k_fake_cells, n_cells, st, seed, first_cell, n_cells, (uint32_t)cell_size, (uint8_t*)d_out);
+  return CDX_OK;
+}
+
 extern "C" int cdx_fake_cells_dev(cdx_ctx* ctx, uint64_t seed, uint64_t first_cell, size_t n_cells, size_t cell_size, void* d_out, void* stream) {
   if (!ctx || !d_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
   if (cell_size == 0 || cell_size % 4 || cell_size > (1u << 30)) return fail(ctx, CDX_ERR_SIZE, "cell size must be a non-zero multiple of 4");
   if (n_cells == 0) return CDX_OK;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  LAUNCH(ctx, k_fake_cells, n_cells, st, seed, first_cell, n_cells, (uint32_t)cell_size, (uint8_t*)d_out);
-  return CDX_OK;
+  return launch_fake_cells(ctx, seed, first_cell, n_cells, cell_size, d_out, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
 extern "C" int cdx_fake_cells_host(cdx_ctx* ctx, uint64_t seed, uint64_t first_cell, size_t n_cells, size_t cell_size, uint8_t* out) {
@@ -1203,7 +1207,10 @@ extern "C" int cdx_fill_synthetic_dev(cdx_ctx* ctx, uint64_t seed, uint64_t firs
   if (!ctx || !d_out) return fail(ctx, CDX_ERR_ARG, "null pointer");
   if (n_bytes % 8) return fail(ctx, CDX_ERR_SIZE, "synthetic fill needs a multiple of 8 bytes");
   if (n_bytes == 0) return CDX_OK;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return launch_fill_synthetic(ctx, seed, first_word, n_bytes, d_out, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+static int launch_fill_synthetic(cdx_ctx* ctx, uint64_t seed, uint64_t first_word, size_t n_bytes, void* d_out, cudaStream_t st) {
   const size_t n_words = n_bytes / 8;
   size_t blocks = (n_words + 255) / 256;
   const size_t cap = (size_t)ctx->sm_count * 32;
@@ -1249,3 +1256,5 @@ extern "C" int cdx_probe_imad_rate(cdx_ctx* ctx, int kind, double* ops_per_secon
   if (elapsed_ms) *elapsed_ms = best;
   return CDX_OK;
 }
+
+#include "capi_multi.cuh"

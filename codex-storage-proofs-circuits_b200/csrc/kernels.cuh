@@ -234,6 +234,37 @@ __global__ void __launch_bounds__(CDX_BLOCK) k_merkle_level(const uint8_t* __res
   st_felt(out + 32 * i, from_mont(compress_keyed(x, y, key)));
 }
 
+// K3b: one level of MANY Merkle trees at once -- the slot trees of a batch of small slots.  The level-l nodes of all trees
+// are stored tree after tree; in_off / out_off (n_trees + 1 entries each) are the prefix sums of the per-tree widths at
+// the input and the output level.  Per tree the rules are those of k_merkle_level: a trailing single child is paired
+// with 0 under key bottom+2, which also gives a one-leaf tree its key-3 compression at the bottom level; a tree that
+// has already reached its root has output width 0 and is skipped.  A tree's root (output width 1) is also copied to
+// roots[tree].                                                      merkle/bn254.nim:29-60, gen_input/bn254.nim:41-47
+__global__ void __launch_bounds__(CDX_BLOCK) k_merkle_level_seg(const uint8_t* __restrict__ in, const uint64_t* __restrict__ in_off,
+                                                                uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, uint32_t n_trees,
+                                                                uint32_t bottom, uint8_t* __restrict__ roots) {
+  CDX_KERNEL_PROLOGUE();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_off[n_trees]) return;
+  uint32_t lo = 0, hi = n_trees;                     // largest t with out_off[t] <= i (empty trees share their offset with the next one)
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (out_off[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  const uint64_t j = i - out_off[lo], base = in_off[lo], n = in_off[lo + 1] - base;
+  const Fr x = to_mont(ld_felt(in + 32 * (base + 2 * j)));
+  Fr y = fr_zero();
+  uint32_t key = bottom + 2u;
+  if (2 * j + 1 < n) {
+    y = to_mont(ld_felt(in + 32 * (base + 2 * j + 1)));
+    key = bottom;
+  }
+  const Fr h = from_mont(compress_keyed(x, y, key));
+  st_felt(out + 32 * i, h);
+  if (out_off[lo + 1] - out_off[lo] == 1) st_felt(roots + 32 * (size_t)lo, h);
+}
+
 // K4: batched path gather.  One thread per (sample, level, 16-byte half).  Pure data movement.
 //                                                                 merkle.nim:21-42,86-100, types.nim:27-37
 struct PathPlan {

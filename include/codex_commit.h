@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CDX_ABI_VERSION 1
+#define CDX_ABI_VERSION 2
 #define CDX_FELT_BYTES 32
 
 typedef enum cdx_status {
@@ -98,6 +98,12 @@ int cdx_merkle_layers_host(cdx_ctx* ctx, const uint8_t* leaves, size_t n, int bo
 
 /* Root only.  Replaces: Merkle.digest / merkleDigestBN254 -- nim/merkle/bn254.nim:20, testvectors.nim:56. */
 int cdx_merkle_root_host(cdx_ctx* ctx, const uint8_t* leaves, size_t n, uint8_t root_out[32]);
+
+/* Merkle.digest over a byte string: the bytes are chunked into field elements exactly like a cell (31-byte little-endian
+ * chunks of data ++ 0x01 ++ 0x00.., floor(len/31)+1 elements) and those elements are the leaves of the tree.
+ * Replaces: Merkle.digest(openArray[byte]) -- reference/nim/testvectors/src/testvectors.nim:60-66 (n = 0..80). */
+int cdx_merkle_root_bytes_host(cdx_ctx* ctx, const uint8_t* data, size_t len, uint8_t root_out[32]);
+
 
 /* ---- slot commitment ------------------------------------------------------------------------------------ */
 
@@ -184,6 +190,137 @@ int cdx_slot_prove_batch(const cdx_slot* slot, const uint8_t* entropies, size_t 
  * mergeMerkleProofs, :88-89); same semantics as RootFromMerklePath, circuit/codex/merkle.circom:44-114. */
 int cdx_reconstruct_roots_host(cdx_ctx* ctx, const uint8_t* leaves, const uint64_t* indices, uint64_t n_leaves, const uint8_t* paths,
                                size_t path_stride, size_t depth, size_t n, uint8_t* roots_out);
+
+/* ---- many small slots in one pass ------------------------------------------------------------------------ */
+
+/* n_slots slots stored back to back (slot k is slot_bytes[k] bytes, a non-zero multiple of block_size) committed with ONE
+ * cell-sponge launch, one launch per block-tree level over the whole forest and one launch per slot-tree level over all
+ * slot trees at once (per-slot widths, per-slot odd-node rule, singleton rule for one-block slots); the n_slots roots are
+ * read back once.  A 4 MiB slot alone occupies a B200 for ~2.5 ms with 64 warps; a thousand of them batched run at the
+ * large-slot rate.  Only roots are produced (commit the slot that has to be sampled on its own).
+ * Replaces: the `for i in 0..<nslots: buildSlotTree(...)` loop -- nim/gen_input/bn254.nim:41-47. */
+int cdx_slots_commit_batch_dev(cdx_ctx* ctx, const void* d_data, const uint64_t* slot_bytes, size_t n_slots, size_t cell_size,
+                               size_t block_size, void* stream, uint8_t* roots_out);
+int cdx_slots_commit_batch_host(cdx_ctx* ctx, const uint8_t* data, const uint64_t* slot_bytes, size_t n_slots, size_t cell_size,
+                                size_t block_size, uint8_t* roots_out);
+/* the same over the reference's fake data: slot k has seed seeds[k] and n_cells cells.
+ * Replaces: slotCfgFromDataSetCfg + buildSlotTree per slot -- nim/dataset.nim:32-43, nim/gen_input/bn254.nim:41-47. */
+int cdx_slots_commit_batch_fake(cdx_ctx* ctx, const uint64_t* seeds, size_t n_slots, size_t n_cells, size_t cell_size, size_t block_size,
+                                uint8_t* roots_out);
+
+/* ---- several GPUs: communicators, sharded slots ------------------------------------------------------------
+ * One rank per GPU (one process per GPU, or one thread per GPU inside one process).  The only exchanges on this path are
+ * (a) the level-top_level nodes of a block-range-sharded slot, (b) the 32-byte slot roots of a dataset and (c) the
+ * answer to a challenge travelling from the rank(s) that hold the sampled cells -- a few KB each.  They run over NCCL
+ * (NVLink/NVSwitch) inside the library, on the slot's stream, without a host round trip.  libnccl.so.2 is resolved at run
+ * time (dlopen; an already loaded copy, e.g. PyTorch's, is reused); a single rank needs no NCCL at all.
+ * The reference is single-process and single-threaded: these entry points have no counterpart there beyond the loops
+ * they parallelise (nim/gen_input/bn254.nim:21-30,41-51). */
+typedef struct cdx_comm cdx_comm;
+#define CDX_COMM_ID_BYTES 128
+/* rank 0 creates the id and hands it to the other ranks by any host-side means (ncclGetUniqueId) */
+int cdx_comm_unique_id(uint8_t id_out[CDX_COMM_ID_BYTES]);
+/* collective over all ranks: joins ctx's GPU to the communicator (ncclCommInitRank).  n_ranks == 1 never touches NCCL. */
+int cdx_comm_init_rank(cdx_ctx* ctx, int n_ranks, int rank, const uint8_t id[CDX_COMM_ID_BYTES], cdx_comm** out);
+void cdx_comm_destroy(cdx_comm* comm);
+int cdx_comm_rank(const cdx_comm* comm);
+int cdx_comm_size(const cdx_comm* comm);
+/* barrier on the device: returns when every rank's stream has reached this point (a 4-byte all-reduce + stream sync) */
+int cdx_comm_barrier(cdx_comm* comm);
+
+/* Split a slot of n_total_blocks blocks over n_ranks: picks the exchange level T (the largest one that still balances
+ * the ranks within 1 %) and a contiguous 2^T-aligned block range per rank.  Ranks of a slot with fewer chunks than ranks
+ * get an empty range (n_blocks[r] == 0) and still take part in every collective.   */
+int cdx_plan_block_ranges(uint64_t n_total_blocks, int n_ranks, int* top_level, uint64_t* first_block, uint64_t* n_blocks);
+/* The exchange level caller-chosen ranges allow: the largest T such that every range starts on a multiple of 2^T and
+ * every range but the one ending the slot is a multiple of 2^T long. */
+int cdx_block_ranges_top_level(uint64_t n_total_blocks, int n_ranks, const uint64_t* first_block, const uint64_t* n_blocks, int* top_level);
+
+/* Sharded commitment in one call: this rank's block range (n_local_bytes may be 0: empty shard, data may then be NULL) is
+ * committed up to level top_level, the level-top_level nodes of all ranks are combined on the device (one NCCL collective
+ * on the slot's stream, no host synchronisation) and the replicated top tree is built.  Collective: every rank of `comm`
+ * calls it with the same n_total_blocks and top_level.  The handle then answers cdx_slot_root on every rank and
+ * cdx_slot_cell_paths_sharded / cdx_slot_prove_batch_sharded collectively. */
+int cdx_slot_commit_sharded_dev(cdx_ctx* ctx, cdx_comm* comm, const void* d_data, size_t n_local_bytes, size_t cell_size, size_t block_size,
+                                uint64_t first_block, uint64_t n_total_blocks, int top_level, void* stream, cdx_slot** out);
+int cdx_slot_commit_sharded_host(cdx_ctx* ctx, cdx_comm* comm, const uint8_t* data, size_t n_local_bytes, size_t cell_size, size_t block_size,
+                                 uint64_t first_block, uint64_t n_total_blocks, int top_level, cdx_slot** out);
+/* the exchange alone, for a slot committed with cdx_slot_commit_range_* (asynchronous on the slot's stream) */
+int cdx_slot_exchange_top(cdx_slot* slot, cdx_comm* comm);
+/* cdx_slot_cell_paths / cdx_slot_prove_batch for a sharded slot: every rank passes the same arguments and receives the
+ * complete answer (the owner of a cell fills its path, the ranks' partial results are summed byte-wise on the device). */
+int cdx_slot_cell_paths_sharded(const cdx_slot* slot, cdx_comm* comm, const uint64_t* cell_indices, size_t n_samples, size_t max_depth,
+                                uint8_t* out, uint8_t* leaf_out);
+int cdx_slot_prove_batch_sharded(const cdx_slot* slot, cdx_comm* comm, const uint8_t* entropies, size_t n_challenges, size_t n_samples,
+                                 size_t max_depth, uint64_t* indices_out, uint8_t* paths_out, uint8_t* leaves_out);
+
+/* ---- dataset commitment ------------------------------------------------------------------------------------ */
+
+typedef enum cdx_source_kind {
+  CDX_SRC_FAKE = 0,      /* the reference's fake data: genFakeCell with this seed (nim/slot.nim:23-32) */
+  CDX_SRC_SYNTHETIC = 1, /* counter-based benchmark bytes: word i = splitmix64(seed + i) (cdx_fill_synthetic_dev) */
+  CDX_SRC_FILE = 2,      /* a slot data file, read from offset 0 (nim/dataset.nim:34: <base><k>.dat) */
+  CDX_SRC_HOST = 3       /* bytes in host memory */
+} cdx_source_kind;
+
+typedef struct cdx_slot_desc {   /* one slot of a dataset (SlotConfig, nim/types.nim:75-79) */
+  uint32_t kind;                 /* cdx_source_kind */
+  uint32_t reserved;
+  uint64_t seed;                 /* CDX_SRC_FAKE / CDX_SRC_SYNTHETIC */
+  const char* path;              /* CDX_SRC_FILE */
+  const uint8_t* host;           /* CDX_SRC_HOST */
+  uint64_t n_bytes;              /* slot size: a non-zero multiple of block_size */
+} cdx_slot_desc;
+
+typedef struct cdx_dataset cdx_dataset;
+
+/* Commit every slot of a dataset and build the dataset tree over the slot roots.  With a communicator (may be NULL = one
+ * GPU) the slots are dealt to the ranks by longest-processing-time bin packing, slots that would unbalance the ranks are
+ * block-range-sharded over all of them, small slots are committed in batches, the 32-byte roots are combined with ONE
+ * collective and every rank builds the (tiny) dataset tree.  Collective: every rank passes the same arguments.
+ * keep_slot (or -1): that slot's commitment is retained for cdx_dataset_prove.
+ * Replaces: the slot loop, dataset tree and slot proof of generateProofInput -- nim/gen_input/bn254.nim:41-51;
+ * reference/haskell/src/Sampling.hs:66-70,84. */
+int cdx_dataset_commit(cdx_ctx* ctx, cdx_comm* comm, const cdx_slot_desc* slots, size_t n_slots, size_t cell_size, size_t block_size,
+                       int64_t keep_slot, cdx_dataset** out);
+void cdx_dataset_free(cdx_dataset* ds);
+int cdx_dataset_root(const cdx_dataset* ds, uint8_t root_out[32]);
+/* all slot roots, n_slots * 32 bytes */
+int cdx_dataset_slot_roots(const cdx_dataset* ds, uint8_t* roots_out);
+/* merkleProof(dsetTree, slot_index) zero-padded to max_log2_nslots elements -- nim/gen_input/bn254.nim:50-51, nim/types.nim:27-37 */
+int cdx_dataset_slot_proof(const cdx_dataset* ds, uint64_t slot_index, size_t max_log2_nslots, uint8_t* path_out);
+/* bytes this rank hashed, how many slots it committed whole / in batches / as shards (diagnostics for the bench line) */
+int cdx_dataset_stats(const cdx_dataset* ds, uint64_t* bytes_local, uint32_t* n_whole, uint32_t* n_batched, uint32_t* n_sharded);
+/* The kept slot's handle on this rank: the whole slot on its owner, a shard on every rank if it was sharded, NULL elsewhere. */
+cdx_slot* cdx_dataset_kept_slot(const cdx_dataset* ds);
+/* Answer one challenge against the kept slot: cell indices from (entropy, slot root), cell hashes and merged, padded
+ * Merkle paths.  Collective when the dataset was committed with a communicator; every rank receives the answer.
+ * Replaces: cellIndices + the per-sample proof loop -- nim/sample/bn254.nim:26-27, nim/gen_input/bn254.nim:53-74. */
+int cdx_dataset_prove(const cdx_dataset* ds, const uint8_t entropy[32], size_t n_samples, size_t max_depth, uint64_t* indices_out,
+                      uint8_t* paths_out, uint8_t* leaves_out);
+
+/* ---- all GPUs of one process -------------------------------------------------------------------------------
+ * For a single-process host (the Nim cli, the C++ mirror): a group owns one context and one communicator rank per
+ * device and runs every collective call on one worker thread per GPU.  Results are those of rank 0. */
+typedef struct cdx_group cdx_group;
+/* devices == NULL or n_devices <= 0: every visible GPU */
+int cdx_group_create(const int* devices, int n_devices, cdx_group** out);
+void cdx_group_destroy(cdx_group* group);
+int cdx_group_size(const cdx_group* group);
+cdx_ctx* cdx_group_ctx(const cdx_group* group, int rank);
+cdx_comm* cdx_group_comm(const cdx_group* group, int rank);
+const char* cdx_group_last_error(const cdx_group* group);
+/* one slot in host memory, block-range-sharded over the group's GPUs; slots_out receives cdx_group_size handles */
+int cdx_group_slot_commit_host(cdx_group* group, const uint8_t* data, size_t n_bytes, size_t cell_size, size_t block_size, cdx_slot** slots_out);
+int cdx_group_slot_cell_paths(cdx_group* group, cdx_slot* const* slots, const uint64_t* cell_indices, size_t n_samples, size_t max_depth,
+                              uint8_t* out, uint8_t* leaf_out);
+void cdx_group_slots_free(cdx_group* group, cdx_slot** slots);
+/* cdx_dataset_commit / cdx_dataset_prove on every GPU of the group; datasets_out receives cdx_group_size handles */
+int cdx_group_dataset_commit(cdx_group* group, const cdx_slot_desc* slots, size_t n_slots, size_t cell_size, size_t block_size,
+                             int64_t keep_slot, cdx_dataset** datasets_out);
+int cdx_group_dataset_prove(cdx_group* group, cdx_dataset* const* datasets, const uint8_t entropy[32], size_t n_samples, size_t max_depth,
+                            uint64_t* indices_out, uint8_t* paths_out, uint8_t* leaves_out);
+void cdx_group_datasets_free(cdx_group* group, cdx_dataset** datasets);
 
 /* ---- sampling and data source --------------------------------------------------------------------------- */
 

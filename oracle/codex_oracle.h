@@ -21,6 +21,8 @@ extern "C" {
 /* Poseidon2 t=3 permutation                       reference/haskell/src/Poseidon2/Permutation.hs:40-45 */
 void orc_permutation(const uint8_t in[96], uint8_t out[96]);
 void orc_permutation_batch(const uint8_t *in, uint8_t *out, size_t n);
+/* unit-test hook: a^2 mod r (standard form in and out) through fr_sqr and through fr_mul(a, a) */
+void orc_fr_sqr_check(const uint8_t a[32], uint8_t out_sqr[32], uint8_t out_mul[32]);
 
 /* rate-1 / rate-2 sponge over n field elements    reference/haskell/src/Poseidon2/Sponge.hs:13-43
  * returns 0, or -1 if rate is not 1 or 2 / an element is >= r */

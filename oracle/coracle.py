@@ -37,12 +37,30 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+def use_native() -> bool:
+    """Switch to a build tuned for THIS machine (-O3 -march=native), compiled here and now; used by bench.py's CPU legs so
+    that the reported baseline is not handicapped by generic code.  Returns False (and keeps the portable build) if the
+    compiler is missing or the build fails."""
+    global _SO, _lib
+    native = os.path.join(_HERE, "build", "libcodex_oracle_native.so")
+    try:
+        if os.path.exists(native):
+            os.remove(native)                      # never trust a copy that travelled from another machine
+        subprocess.run(["make", "-C", _HERE, "-s", "native"], check=True, capture_output=True)
+        C.CDLL(native)
+    except Exception:
+        return False
+    _SO, _lib = native, None
+    return True
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(_SO):
             build()
         L = C.CDLL(_SO)
+        L.orc_fr_sqr_check.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
         u8p, sz, u64 = C.c_char_p, C.c_size_t, C.c_uint64
         L.orc_permutation.argtypes = [u8p, u8p]
         L.orc_permutation_batch.argtypes = [u8p, u8p, sz]
@@ -80,6 +98,13 @@ def pack(xs: Sequence[int]) -> bytes:
 
 def unpack(buf: bytes) -> List[int]:
     return [int.from_bytes(buf[i:i + 32], "little") for i in range(0, len(buf), 32)]
+
+
+def fr_sqr_check(a: int) -> Tuple[int, int]:
+    """(a^2 mod r via the dedicated squaring, via the general product)"""
+    o1, o2 = C.create_string_buffer(32), C.create_string_buffer(32)
+    lib().orc_fr_sqr_check(f2b(a), o1, o2)
+    return b2f(o1.raw), b2f(o2.raw)
 
 
 def permutation(s: Sequence[int]) -> Tuple[int, int, int]:

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.capi.LIB_PATH)
     for name in header_functions():
         assert getattr(lib, name) is not None, name
-    assert pkg.load_library().cdx_abi_version() == 1
+    assert pkg.load_library().cdx_abi_version() == 2
 
 
 def test_pure_host_helpers(pkg):
@@ -73,3 +73,16 @@ def test_header_is_plain_c(tmp_path):
         res = subprocess.run([cc, std, "-Wall", "-Werror", "-pedantic", "-x", "c" if cc == "gcc" else "c++", "-I", hdr, "-c", str(src), "-o",
                               str(tmp_path / "use.o")], capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
+
+
+def test_planners_and_comm_without_a_gpu(pkg):
+    """host-only entry points of the multi-GPU half of the ABI: the range planners need no device; a one-rank communicator
+    needs a context (so a GPU), and asking for several ranks without NCCL's id is an argument error, not a crash"""
+    t, ranges = pkg.capi.plan_block_ranges(1638400, 8)
+    assert t == 13 and ranges[7] == (7 * 204800, 204800)
+    t, ranges = pkg.capi.plan_block_ranges(3, 4)                       # fewer chunks than ranks: empty shards
+    assert t == 0 and sorted(c for _, c in ranges) == [0, 1, 1, 1]
+    assert pkg.capi.block_ranges_top_level(1 << 20, [(0, 1 << 19), (1 << 19, 1 << 19)]) == 19
+    lib = pkg.load_library()
+    assert lib.cdx_comm_rank(None) == 0 and lib.cdx_comm_size(None) == 1
+    assert lib.cdx_group_size(None) == 0 and lib.cdx_dataset_kept_slot(None) is None

@@ -59,10 +59,17 @@ def test_testvector_suite(ctx, vectors, pkg):
 
 
 def test_byte_merkle_roots(ctx, orc, vectors):
-    """Merkle.digest(bytes): chunk on the host side of the ABI (pure byte shuffling), tree on the GPU (testvectors.nim:60-66)."""
-    for n in range(0, 81, 7):
-        elems = orc.bytes_to_elements(bytes(range(1, n + 1)))     # byte chunking only
-        assert str(ctx.merkle_root(elems)) == vectors["merkle_root_bytes"][n]
+    """Merkle.digest(openArray[byte]) through its own entry point, cdx_merkle_root_bytes_host: chunking and tree both on the
+    GPU, every n = 0..80 of testvectors.nim:60-66, against the golden values and the oracle"""
+    for n in range(0, 81):
+        data = bytes(range(1, n + 1))
+        got = ctx.merkle_root_bytes(data)
+        assert str(got) == vectors["merkle_root_bytes"][n], n
+        assert got == orc.merkle_root(orc.bytes_to_elements(data)), n
+    rnd = random.Random(61)
+    for n in (31, 62, 93, 2048, 5000):                            # chunk-boundary lengths and a multi-level tree
+        data = bytes(rnd.randrange(256) for _ in range(n))
+        assert ctx.merkle_root_bytes(data) == orc.merkle_root(orc.bytes_to_elements(data)), n
 
 
 def test_sponge_batches_random(ctx, orc):

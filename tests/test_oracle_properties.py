@@ -52,3 +52,16 @@ def test_subtree_composition(orc_mod, leaves):
 @given(felts, felts, st.integers(min_value=0, max_value=3))
 def test_compress_is_the_first_permutation_word(orc_mod, x, y, key):
     assert orc_mod.compress(x, y, key) == orc_mod.permutation((x, y, key))[0]
+
+
+def test_oracle_dedicated_squaring(orc):
+    """the oracle's 10-product squaring (CPU baseline honesty) equals its general product and a^2 mod r"""
+    import random
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    rnd = random.Random(2)
+    cases = [0, 1, 2, R - 1, R - 2, (1 << 64) - 1, (1 << 128) - 1, (1 << 192) - 1, (1 << 253), (1 << 254) % R, 0xffffffffffffffff << 64]
+    cases += [rnd.randrange(R) for _ in range(5000)]
+    cases += [int("ffffffffffffffff" * k + "0000000000000000" * (3 - k) + "00000000ffffffff", 16) % R for k in range(4)]
+    for a in cases:
+        s, m = orc.fr_sqr_check(a)
+        assert s == m == a * a % R, hex(a)

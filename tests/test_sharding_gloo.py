@@ -1,7 +1,10 @@
-"""The N > 1 path on CPU: world_size-2 gloo run of the block-range sharding orchestration
-(codex-storage-proofs-circuits_b200/sharded.py) with an oracle-backed stand-in for the per-rank GPU slot.  What is
-under test is the host logic that is identical on GPUs: range planning, the global odd-node rule at the ragged tail,
-the padded all-gather and compaction of sub-tree roots, the replicated top tree, and owner-only path assembly."""
+"""The N > 1 path on CPU: world_size-2 gloo run of the block-range sharding PROTOCOL the library implements over NCCL
+(csrc/capi_multi.cuh: cdx_slot_exchange_top, prove_core), with an oracle-backed stand-in for the per-rank GPU slot and
+torch.distributed/gloo standing in for NCCL.  What is under test is everything that does not depend on the device: range
+planning (Python twin == the C planner), the global odd-node rule at the ragged tail, the exchange -- every rank places its
+level-T nodes at their global positions in a zeroed level and ONE byte-wise SUM combines them --, the replicated top tree,
+owner-only path assembly combined by the same byte-wise SUM, empty shards, and the communicator bootstrap
+(sharded.comm_from_torch) up to the point where it needs a GPU."""
 import importlib
 import os
 import sys
@@ -41,6 +44,8 @@ class OracleShard:
 
     def subtree_roots_tensor(self, device="cpu"):
         raw = b"".join(int(v).to_bytes(32, "little") for v in self.low[self.T])
+        if not raw:                                      # empty shard
+            return torch.zeros(0, dtype=torch.uint8)
         return torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
 
     def set_top_tensor(self, t):
@@ -82,6 +87,30 @@ class OracleShard:
         return paths, leaves
 
 
+def exchange_top_model(shard, n_total_blocks, top_level):
+    """cdx_slot_exchange_top, line by line: zeroed level T, own nodes in place, byte-wise SUM over the ranks, top tree"""
+    sharded = importlib.import_module(PKG + ".sharded")
+    width = sharded.level_width(n_total_blocks, top_level)
+    lvl = torch.zeros(32 * width, dtype=torch.uint8)
+    own = shard.subtree_roots_tensor()
+    first_node = shard.first >> top_level
+    lvl[32 * first_node:32 * first_node + own.numel()] = own
+    dist.all_reduce(lvl, op=dist.ReduceOp.SUM)
+    shard.set_top_tensor(lvl)
+
+
+def gather_paths_model(shard, indices, max_depth):
+    """prove_core's combine: the owner fills a cell's path and leaf, everyone else zeros, byte-wise SUM"""
+    paths, leaves = shard.cell_paths(list(indices), max_depth)
+    flat = b"".join(int(v).to_bytes(32, "little") for p in paths for v in p) + b"".join(int(v).to_bytes(32, "little") for v in leaves)
+    t = torch.frombuffer(bytearray(flat), dtype=torch.uint8).clone()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    raw = bytes(t.numpy())
+    n = len(indices)
+    vals = [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
+    return [vals[i * max_depth:(i + 1) * max_depth] for i in range(n)], vals[n * max_depth:]
+
+
 def _worker(rank, world, port, n_total_blocks, seed, out_q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -91,16 +120,16 @@ def _worker(rank, world, port, n_total_blocks, seed, out_q):
         from oracle import coracle as orc
         top_level, ranges = sharded.plan_block_ranges(n_total_blocks, world, max_imbalance=0.35)
         first, count = ranges[rank]
-        shard = OracleShard(orc, seed, first, count, n_total_blocks, top_level)
-        sharded.exchange_subtree_roots(shard, n_total_blocks, top_level, ranges, device="cpu")
-        indices = [0, 31, 32 * (n_total_blocks // 2), 32 * n_total_blocks - 1, 32 * (n_total_blocks - 1)]
-        paths, leaves = sharded.gather_cell_paths(shard, indices, 16, device="cpu")
+        shard = OracleShard(orc, seed, first, count, n_total_blocks, top_level)       # count == 0: an empty shard
+        exchange_top_model(shard, n_total_blocks, top_level)
+        indices = sorted({0, 31, 32 * (n_total_blocks // 2), 32 * n_total_blocks - 1, 32 * (n_total_blocks - 1)})
+        paths, leaves = gather_paths_model(shard, indices, 16)
         out_q.put((rank, top_level, ranges, shard.root, indices, paths, leaves))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total_blocks", [13, 16, 21])
+@pytest.mark.parametrize("n_total_blocks", [13, 16, 21, 1])
 def test_two_rank_sharded_commit_matches_single_process(orc, n_total_blocks):
     seed, world = 777, 2
     ctx = mp.get_context("spawn")
@@ -109,7 +138,7 @@ def test_two_rank_sharded_commit_matches_single_process(orc, n_total_blocks):
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_total_blocks, seed, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=300) for _ in range(world)]
+    results = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -130,8 +159,10 @@ def test_two_rank_sharded_commit_matches_single_process(orc, n_total_blocks):
 
 def test_range_planning_properties(pkg):
     sharded = importlib.import_module(PKG + ".sharded")
-    for n_blocks, world in [(1638400, 8), (163840, 1), (163840, 3), (5, 8), (1, 2), (2097152, 8), (1000, 7)]:
+    for n_blocks, world in [(1638400, 8), (163840, 1), (163840, 3), (5, 8), (1, 2), (2097152, 8), (1000, 7), (1, 1), (3, 2), (655360, 4)]:
         t, ranges = sharded.plan_block_ranges(n_blocks, world)
+        assert (t, ranges) == pkg.capi.plan_block_ranges(n_blocks, world)      # the C planner (cdx_plan_block_ranges) is the one that ships
+        assert pkg.capi.block_ranges_top_level(n_blocks, ranges) >= t
         assert len(ranges) == world and sum(c for _, c in ranges) == n_blocks
         pos = 0
         for f, c in ranges:
@@ -146,6 +177,9 @@ def test_range_planning_properties(pkg):
     assert t == 13 and all(c == 204800 for _, c in ranges)         # 25 chunks of 8192 blocks per GPU
     t, ranges = sharded.fixed_ranges(163840, 8)                    # bench.py weak-scaling layout
     assert t == 15 and ranges[3] == (3 * 163840, 163840)
+    assert pkg.capi.block_ranges_top_level(8 * 163840, ranges) == 15
+    with pytest.raises(pkg.CodexCommitError):
+        pkg.capi.block_ranges_top_level(100, [(0, 40), (50, 50)])     # a gap
     assert sharded.level_width(163840, 15) == 5 and sharded.level_width(5, 3) == 1
 
 
