@@ -25,17 +25,23 @@ using namespace cdx;
 
 // ---------------------------------------------------------------------------------------------------------
 
+#define CDX_MAX_STAGE 4
+
 struct cdx_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // H2D staging for *_host entry points
+  cudaStream_t copy_stream2 = nullptr; // second H2D stream: the copies of consecutive tiles of a pinned slot alternate (two in flight)
   cudaStream_t stream2 = nullptr;      // second compute stream: odd tiles of a host-resident slot (kernels overlap at the tile seams)
   cudaEvent_t ev_join = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
-  void* d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[CDX_MAX_STAGE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_consumed[CDX_MAX_STAGE] = {nullptr, nullptr, nullptr, nullptr};
+  void* d_stage[CDX_MAX_STAGE] = {nullptr, nullptr, nullptr, nullptr};   // device tiles the non-resident pipelines stream through
   size_t stage_bytes = 0;
+  int stage_count = 0;
+  int stage_tiles = 3;                 // tiles in flight for pinned host slots (CODEX_COMMIT_STAGE_TILES = 2..4)
+  size_t tile_mib = 256;               // tile size of the non-resident pipelines (CODEX_COMMIT_TILE_MIB)
   void* h_pinned[2] = {nullptr, nullptr};   // pinned read buffers of cdx_slot_commit_file
   size_t pinned_bytes = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
@@ -83,9 +89,20 @@ static int fail(cdx_ctx* ctx, int status, const char* fmt, ...) {
 
 static inline unsigned grid_for(size_t n, unsigned block = CDX_BLOCK) { return (unsigned)((n + block - 1) / block); }
 
+// CTA width for a launch of n threads: the compiled width when the launch fills the machine, narrower CTAs (down to one
+// warp) when it does not, so that a small launch -- a 4 MiB slot is 2048 cells, the upper tree levels a handful of nodes --
+// spreads over as many SMs as it has warps.  Every thread of these kernels runs a long dependent chain of
+// multiplications; two warps sharing an SM sub-partition finish later than two warps on two SMs.
+static inline unsigned block_for(const cdx_ctx* ctx, size_t n) {
+  unsigned b = CDX_BLOCK;
+  while (b > 32 && n < (size_t)ctx->sm_count * b) b >>= 1;
+  return b;
+}
+
 #define LAUNCH(ctx, kernel, n_threads, stream, ...)                                    \
   do {                                                                                 \
-    kernel<<<grid_for(n_threads), CDX_BLOCK, 0, (stream)>>>(__VA_ARGS__);              \
+    const unsigned _b = block_for((ctx), (n_threads));                                 \
+    kernel<<<grid_for((n_threads), _b), _b, 0, (stream)>>>(__VA_ARGS__);               \
     (ctx)->launches++;                                                                 \
     CU_TRY(ctx, cudaGetLastError());                                                   \
   } while (0)
@@ -118,6 +135,14 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   ctx->device = device;
   if (const char* v = getenv("CODEX_COMMIT_PLAIN_LOADS")) ctx->plain_loads = v[0] == '1';
   if (const char* v = getenv("CODEX_COMMIT_NO_BOUNCE")) ctx->no_bounce = v[0] == '1';
+  if (const char* v = getenv("CODEX_COMMIT_STAGE_TILES")) {
+    const int n = atoi(v);
+    if (n >= 2 && n <= CDX_MAX_STAGE) ctx->stage_tiles = n;
+  }
+  if (const char* v = getenv("CODEX_COMMIT_TILE_MIB")) {
+    const long n = atol(v);
+    if (n >= 16 && n <= 4096) ctx->tile_mib = (size_t)n;
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) {   // keep freed tree buffers in the pool instead of returning them to the driver
@@ -130,13 +155,14 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+  for (int i = 0; i < CDX_MAX_STAGE && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
   }
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete ctx;
     return CDX_ERR_CUDA;
@@ -148,13 +174,16 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
 extern "C" void cdx_ctx_destroy(cdx_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < CDX_MAX_STAGE; ++i) {
     if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
-    if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
-    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
   }
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+  }
+  if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -210,9 +239,11 @@ static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, s
     // tensor coordinates are signed 32-bit (a row index >= 2^31 would read as out of bounds, i.e. as zeros): launches of at
     // most 2^30 cells, each with its own tensor-map base
     const size_t max_cells = (size_t)1 << 30;
-    const size_t smem = 128 + (CDX_BLOCK / 32) * (CDX_RING_SLOTS * CDX_BOX_BYTES + 8 * CDX_RING_SLOTS);
-    if (smem > 48 * 1024 && !ctx->tma_smem_set) {   // per device, once: rings of CTAs wider than 7 warps exceed the default 48 KB
-      CU_TRY(ctx, cudaFuncSetAttribute(k_hash_cells_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blk = block_for(ctx, n_cells);
+    const size_t smem_max = 128 + (CDX_BLOCK / 32) * (CDX_RING_SLOTS * CDX_BOX_BYTES + 8 * CDX_RING_SLOTS);
+    const size_t smem = 128 + (blk / 32) * (CDX_RING_SLOTS * CDX_BOX_BYTES + 8 * CDX_RING_SLOTS);
+    if (smem_max > 48 * 1024 && !ctx->tma_smem_set) {   // per device, once: rings of CTAs wider than 7 warps exceed the default 48 KB
+      CU_TRY(ctx, cudaFuncSetAttribute(k_hash_cells_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
       ctx->tma_smem_set = true;
     }
     for (size_t c0 = 0; c0 < n_cells; c0 += max_cells) {
@@ -225,7 +256,7 @@ static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, s
       // CU_TENSOR_MAP_DATA_TYPE_UINT8 = 0, INTERLEAVE_NONE = 0, SWIZZLE_NONE = 0, L2_PROMOTION_NONE = 0, FLOAT_OOB_FILL_NONE = 0 (zeros)
       const int rc = encode(&tmap, 0, 2, (void*)((const uint8_t*)d_data + c0 * cell_size), dims, strides, box, estr, 0, 0, 0, 0);
       if (rc != 0) return fail(ctx, CDX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", rc);
-      k_hash_cells_tma<<<grid_for(nc), CDX_BLOCK, smem, st>>>(tmap, nc, (uint32_t)cell_size, d_out + 32 * c0);
+      k_hash_cells_tma<<<grid_for(nc, blk), blk, smem, st>>>(tmap, nc, (uint32_t)cell_size, d_out + 32 * c0);
       ctx->launches++;
       CU_TRY(ctx, cudaGetLastError());
     }
@@ -234,8 +265,9 @@ static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, s
   const size_t max_cells = (size_t)1 << 30;                                  // keeps the grid below 2^31 CTAs
   for (size_t c0 = 0; c0 < n_cells; c0 += max_cells) {
     const size_t nc = n_cells - c0 < max_cells ? n_cells - c0 : max_cells;
-    k_hash_cells<<<grid_for(nc), CDX_BLOCK, 0, st>>>((const uint32_t*)((const uint8_t*)d_data + c0 * cell_size), nc, (uint32_t)(cell_size / 4),
-                                                    d_out + 32 * c0);
+    const unsigned blk = block_for(ctx, nc);
+    k_hash_cells<<<grid_for(nc, blk), blk, 0, st>>>((const uint32_t*)((const uint8_t*)d_data + c0 * cell_size), nc, (uint32_t)(cell_size / 4),
+                                                   d_out + 32 * c0);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
   }
@@ -598,15 +630,20 @@ extern "C" int cdx_slot_commit_dev(cdx_ctx* ctx, const void* d_data, size_t n_by
   return CDX_OK;
 }
 
-static int ensure_stage(cdx_ctx* ctx, size_t bytes) {
-  if (ctx->stage_bytes >= bytes) return CDX_OK;
-  for (int i = 0; i < 2; ++i) {
+static int ensure_stage(cdx_ctx* ctx, size_t bytes, int count = 2) {
+  if (ctx->stage_bytes >= bytes && ctx->stage_count >= count) return CDX_OK;
+  const size_t want_bytes = bytes > ctx->stage_bytes ? bytes : ctx->stage_bytes;
+  const int want_count = count > ctx->stage_count ? count : ctx->stage_count;
+  CU_TRY(ctx, cudaDeviceSynchronize());                       // earlier calls may still be reading the old tiles
+  for (int i = 0; i < CDX_MAX_STAGE; ++i) {
     if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
     ctx->d_stage[i] = nullptr;
   }
   ctx->stage_bytes = 0;
-  for (int i = 0; i < 2; ++i) CU_TRY(ctx, cudaMalloc(&ctx->d_stage[i], bytes));
-  ctx->stage_bytes = bytes;
+  ctx->stage_count = 0;
+  for (int i = 0; i < want_count; ++i) CU_TRY(ctx, cudaMalloc(&ctx->d_stage[i], want_bytes));
+  ctx->stage_bytes = want_bytes;
+  ctx->stage_count = want_count;
   return CDX_OK;
 }
 
@@ -618,6 +655,7 @@ typedef std::function<void(uint8_t* dst, uint64_t offset, size_t len)> ChunkFill
 
 static void drain_streams(cdx_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->copy_stream2);
   cudaStreamSynchronize(ctx->stream2);
   cudaStreamSynchronize(ctx->stream);
 }
@@ -628,34 +666,39 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   // Tile = 256 MiB: 131 072 cells of 2 KiB, about one full wave of the cell-sponge kernel on 148 SMs (the resident
   // CTAs per SM are set by CDX_TMA_MIN_CTAS in kernels.cuh); smaller tiles leave SMs idle, larger ones only add exposed
   // first-copy latency.  Slots below 1 GiB are cut in four so that the copy still overlaps.
-  size_t tile_bytes_target = (size_t)256 << 20;
+  size_t tile_bytes_target = ctx->tile_mib << 20;
   if (n_bytes < ((size_t)1 << 30)) tile_bytes_target = n_bytes / 4 > ((size_t)16 << 20) ? n_bytes / 4 : ((size_t)16 << 20);
   size_t tile_blocks = tile_bytes_target / block_size;
   if (tile_blocks == 0) tile_blocks = 1;
   if (tile_blocks > n_blocks) tile_blocks = n_blocks;
-  int rc = ensure_stage(ctx, tile_blocks * block_size);
+  const int NS = ctx->stage_tiles;
+  int rc = ensure_stage(ctx, tile_blocks * block_size, NS);
   if (rc) return rc;
   const size_t cpb = block_size / cell_size;
-  // tile t lives in staging buffer t&1 and is hashed on compute stream t&1, so the cell kernels of consecutive
-  // tiles overlap at the seams (the tail of one fills up with the head of the next) while each buffer is still
-  // reused strictly in order: copy(t) waits for hash(t-2), hash(t) waits for copy(t).
+  // Tile t lives in staging buffer t % NS, is copied on copy stream t&1 and hashed on compute stream t&1.  Two compute
+  // streams let the cell kernels of consecutive tiles overlap at the seams (the tail of one fills up with the head of the
+  // next); NS = 3 buffers and two copy streams keep TWO copies in flight ahead of the sponge, which rides out a host
+  // whose PCIe/memory path is shared by eight GPUs streaming at once.  Each buffer is reused strictly
+  // in order: copy(t) waits for hash(t-NS), hash(t) waits for copy(t).
   CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->stream));              // the hash buffer was allocated on stream
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_join, 0));
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));  // and the staging tiles may still be read by earlier work on it
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_join, 0));
   size_t done = 0;
   const size_t first_tile = tile_blocks / 8 ? tile_blocks / 8 : 1;
   const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
   for (int t = 0; done < n_blocks; ++t) {
-    const int b = t & 1;
-    cudaStream_t cs = b ? ctx->stream2 : ctx->stream;
+    const int b = t % NS;
+    cudaStream_t cs = (t & 1) ? ctx->stream2 : ctx->stream;
+    cudaStream_t cp = (t & 1) ? ctx->copy_stream2 : ctx->copy_stream;
     // the copy of tile 0 is the only one nothing overlaps: keep it short (1/8 tile), then realign with tile 1
     size_t want = tile_blocks;
     if (ramp && t == 0) want = first_tile;
     else if (ramp && t == 1) want = tile_blocks - first_tile;
     const size_t nb = n_blocks - done < want ? n_blocks - done : want;
-    if (t >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    if (t >= NS) CU_TRY(ctx, cudaStreamWaitEvent(cp, ctx->ev_consumed[b], 0));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, cp));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], cp));
     CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
     int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, d_hashes + 32 * done * cpb, cs);
     if (hr) return hr;
@@ -672,7 +715,7 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
 // into the current device tile (copy stream), cell sponge per finished tile (alternating compute streams).
 static int hash_cells_staged(cdx_ctx* ctx, size_t n_bytes, size_t cell_size, size_t block_size, const ChunkFill& fill, uint8_t* d_hashes) {
   const size_t n_blocks = n_bytes / block_size;
-  const size_t chunk_bytes_target = (size_t)64 << 20;                       // pinned chunk
+  const size_t chunk_bytes_target = (ctx->tile_mib << 20) / 4;              // pinned chunk
   size_t chunk_blocks = chunk_bytes_target / block_size ? chunk_bytes_target / block_size : 1;
   size_t tile_blocks = 4 * chunk_blocks;                                    // device tile = 4 chunks = 256 MiB (one sponge wave)
   if (tile_blocks > n_blocks) tile_blocks = n_blocks;
@@ -767,7 +810,7 @@ static int generate_bytes(cdx_ctx* ctx, uint32_t kind, uint64_t seed, uint64_t f
 static int hash_cells_generated(cdx_ctx* ctx, uint32_t kind, uint64_t seed, uint64_t first_byte, size_t n_bytes, size_t cell_size, size_t block_size,
                                 uint8_t* d_hashes) {
   const size_t n_blocks = n_bytes / block_size;
-  size_t tile_blocks = ((size_t)256 << 20) / block_size;
+  size_t tile_blocks = (ctx->tile_mib << 20) / block_size;
   if (tile_blocks == 0) tile_blocks = 1;
   if (tile_blocks > n_blocks) tile_blocks = n_blocks;
   int rc = ensure_stage(ctx, tile_blocks * block_size);

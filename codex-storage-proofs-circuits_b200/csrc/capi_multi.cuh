@@ -86,7 +86,8 @@ static int batch_trees(cdx_ctx* ctx, uint8_t* d_forest, size_t n_cells, size_t c
   for (size_t l = 0; l + 1 < n_levels; ++l) {
     const size_t n_out = off[l + 1][n_slots];
     if (n_out > 0xffffffffull * CDX_BLOCK) return fail(ctx, CDX_ERR_SIZE, "batch too large");
-    k_merkle_level_seg<<<grid_for(n_out), CDX_BLOCK, 0, st>>>(in, offs + l * (n_slots + 1), out, offs + (l + 1) * (n_slots + 1), (uint32_t)n_slots,
+    const unsigned blk = block_for(ctx, n_out);
+    k_merkle_level_seg<<<grid_for(n_out, blk), blk, 0, st>>>(in, offs + l * (n_slots + 1), out, offs + (l + 1) * (n_slots + 1), (uint32_t)n_slots,
                                                               l == 0 ? 1u : 0u, d_roots);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -466,6 +467,9 @@ extern "C" int cdx_slot_commit_sharded_dev(cdx_ctx* ctx, cdx_comm* comm, const v
   return CDX_OK;
 }
 
+// the gather kernel moves 16-byte halves: the paths must start 16-byte aligned behind the 8-byte indices
+static size_t prove_idx_region(size_t total) { return (8 * total + 15) & ~(size_t)15; }
+
 // cell indices (optional: from entropies) + path gather + optional byte-wise combine over the ranks + copy back.
 //   d_entropies != null: indices for n_challenges x n_samples are derived on the device from the slot root;
 //   otherwise `cells` (host) holds n_total indices.
@@ -488,8 +492,8 @@ static int prove_core(const cdx_slot* s, cdx_comm* comm, const uint8_t* entropie
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   PathPlan plan;
   make_path_plan(s, plan);
-  // one buffer: [indices 8 B x total | paths 32 B x total x max_depth | leaves 32 B x total]
-  const size_t idx_bytes = 8 * total, path_bytes = 32 * total * max_depth, leaf_bytes = 32 * total;
+  // one buffer: [indices 8 B x total, padded to 16 B | paths 32 B x total x max_depth | leaves 32 B x total]
+  const size_t idx_bytes = prove_idx_region(total), path_bytes = 32 * total * max_depth, leaf_bytes = 32 * total;
   DevBuf d_ent, d_all;
   CU_TRY(ctx, d_all.alloc(idx_bytes + path_bytes + leaf_bytes, s->stream));
   uint64_t* d_idx = (uint64_t*)d_all.p;
@@ -500,7 +504,7 @@ static int prove_core(const cdx_slot* s, cdx_comm* comm, const uint8_t* entropie
     CU_TRY(ctx, cudaMemcpyAsync(d_ent.p, entropies, 32 * n_challenges, cudaMemcpyHostToDevice, s->stream));
     LAUNCH(ctx, k_cell_indices, total, s->stream, d_ent.u8(), (const uint8_t*)s->top[s->slot_depth], n_cells_total - 1, (uint32_t)n_samples, total, d_idx);
   } else {
-    CU_TRY(ctx, cudaMemcpyAsync(d_idx, cells, idx_bytes, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(d_idx, cells, 8 * total, cudaMemcpyHostToDevice, s->stream));
   }
   const size_t threads = total * (max_depth + 1) * 2;
   k_gather_paths<<<grid_for(threads, 256), 256, 0, s->stream>>>(plan, d_idx, (uint32_t)total, (uint32_t)max_depth, d_paths, d_leaves);
@@ -511,7 +515,7 @@ static int prove_core(const cdx_slot* s, cdx_comm* comm, const uint8_t* entropie
     int rc = allreduce_bytes(ctx, comm, d_all.p, idx_bytes + path_bytes + leaf_bytes, s->stream);
     if (rc) return rc;
   }
-  if (indices_out) CU_TRY(ctx, cudaMemcpyAsync(indices_out, d_idx, idx_bytes, cudaMemcpyDeviceToHost, s->stream));
+  if (indices_out) CU_TRY(ctx, cudaMemcpyAsync(indices_out, d_idx, 8 * total, cudaMemcpyDeviceToHost, s->stream));
   CU_TRY(ctx, cudaMemcpyAsync(paths_out, d_paths, path_bytes, cudaMemcpyDeviceToHost, s->stream));
   if (leaves_out) CU_TRY(ctx, cudaMemcpyAsync(leaves_out, d_leaves, leaf_bytes, cudaMemcpyDeviceToHost, s->stream));
   CU_TRY(ctx, cudaStreamSynchronize(s->stream));
@@ -881,15 +885,16 @@ extern "C" int cdx_dataset_prove(const cdx_dataset* ds, const uint8_t entropy[32
   }
   // not the owner: contribute zeros to the same collective and receive the answer
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  const size_t bytes = 8 * n_samples + 32 * n_samples * max_depth + 32 * n_samples;
+  const size_t idx_bytes = prove_idx_region(n_samples);               // the owner's layout (prove_core)
+  const size_t bytes = idx_bytes + 32 * n_samples * max_depth + 32 * n_samples;
   DevBuf d;
   CU_TRY(ctx, d.alloc(bytes, ctx->stream));
   CU_TRY(ctx, cudaMemsetAsync(d.p, 0, bytes, ctx->stream));
   int rc = allreduce_bytes(ctx, ds->comm, d.p, bytes, ctx->stream);
   if (rc) return rc;
   CU_TRY(ctx, cudaMemcpyAsync(indices_out, d.p, 8 * n_samples, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(paths_out, d.u8() + 8 * n_samples, 32 * n_samples * max_depth, cudaMemcpyDeviceToHost, ctx->stream));
-  if (leaves_out) CU_TRY(ctx, cudaMemcpyAsync(leaves_out, d.u8() + 8 * n_samples + 32 * n_samples * max_depth, 32 * n_samples, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(paths_out, d.u8() + idx_bytes, 32 * n_samples * max_depth, cudaMemcpyDeviceToHost, ctx->stream));
+  if (leaves_out) CU_TRY(ctx, cudaMemcpyAsync(leaves_out, d.u8() + idx_bytes + 32 * n_samples * max_depth, 32 * n_samples, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return CDX_OK;
 }

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -141,12 +142,34 @@ std::vector<F> elements(const std::vector<uint8_t>& bytes) {   // 31-byte LE chu
 
 // ---- backend ------------------------------------------------------------------------------------------------
 
-Backend::Backend(int device) {
+Backend::Backend(int device) : device_(device) {
   const int rc = cdx_ctx_create(device, &ctx_);
   if (rc != CDX_OK)
     throw AssertionDefect(std::string("cdx_ctx_create failed: ") + cdx_status_string(rc) + " (this backend needs a CUDA device; there is no CPU path)");
 }
-Backend::~Backend() { cdx_ctx_destroy(ctx_); }
+Backend::~Backend() {
+  cdx_group_destroy(group_);
+  cdx_ctx_destroy(ctx_);
+}
+int Backend::visibleGpus() const {
+  int n = 1;
+  for (cdx_ctx* probe = nullptr; n < 64 && cdx_ctx_create(device_ + n, &probe) == CDX_OK; ++n) cdx_ctx_destroy(probe);
+  if (const char* cap = std::getenv("CODEX_COMMIT_GPUS")) {
+    const int c = std::atoi(cap);
+    if (c >= 1 && c < n) n = c;
+  }
+  return n;
+}
+cdx_group* Backend::group() {
+  if (!group_) {
+    std::vector<int> devs;
+    const int n = visibleGpus();
+    for (int i = 0; i < n; ++i) devs.push_back(device_ + i);
+    const int rc = cdx_group_create(devs.data(), (int)devs.size(), &group_);
+    if (rc != CDX_OK) throw AssertionDefect(std::string("cdx_group_create failed: ") + cdx_status_string(rc));
+  }
+  return group_;
+}
 void Backend::check(int rc, const char* what) const {
   if (rc != CDX_OK) throw AssertionDefect(std::string(what) + ": " + cdx_last_error(ctx_) + " [" + cdx_status_string(rc) + "]");
 }
@@ -342,24 +365,18 @@ Block dataSetLoadBlockData(Backend& be, const GlobalConfig& g, const DataSetConf
 // ---- nim/gen_input/bn254.nim --------------------------------------------------------------------------------
 
 namespace {
-struct SlotHandle {   // RAII over cdx_slot
-  cdx_slot* h = nullptr;
-  ~SlotHandle() { cdx_slot_free(h); }
-};
-
-// buildSlotTree (gen_input/bn254.nim:21-33) as ONE device commitment; every layer stays in HBM inside the handle
-void commitSlot(Backend& be, const GlobalConfig& g, const SlotConfig& cfg, SlotHandle& out) {
-  const int64_t k = cellsPerBlock(g);
-  const int64_t nblocks = cfg.nCells / k;
-  nim_assert(nblocks * k == cfg.nCells && nblocks > 0, "slot size is not divisible by the block size");
-  if (cfg.dataSrc.kind == DataSourceKind::FakeData) {
-    be.check(cdx_slot_commit_fake(be.ctx(), cfg.dataSrc.seed, (size_t)cfg.nCells, (size_t)g.cellSize, (size_t)g.blockSize, &out.h), "buildSlotTree");
-  } else {
-    // straight from the file: pread -> pinned buffers -> H2D -> sponge, overlapped (short files read as zeros, slot.nim:64-65)
-    be.check(cdx_slot_commit_file(be.ctx(), cfg.dataSrc.filename.c_str(), 0, (size_t)(g.cellSize * cfg.nCells), (size_t)g.cellSize,
-                                  (size_t)g.blockSize, &out.h), "buildSlotTree");
+// the dataset committed on one GPU (comm == NULL) or on every GPU of the backend's group: handles per rank
+struct DatasetHandles {
+  Backend& be;
+  cdx_group* group = nullptr;
+  std::vector<cdx_dataset*> ds;
+  explicit DatasetHandles(Backend& b) : be(b) {}
+  ~DatasetHandles() {
+    if (group) cdx_group_datasets_free(group, ds.data());
+    else
+      for (cdx_dataset* d : ds) cdx_dataset_free(d);
   }
-}
+};
 }  // namespace
 
 SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, const GlobalConfig& globCfg, const DataSetConfig& dsetCfg,
@@ -368,50 +385,98 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
   const int64_t nslots = dsetCfg.nSlots, ncells = dsetCfg.nCells;
   const int64_t cpb = cellsPerBlock(globCfg);
   const int64_t nblocks = ncells / cpb;
-  nim_assert(nblocks * cpb == ncells, "slot size is not divisible by the block size");
+  nim_assert(nblocks * cpb == ncells && nblocks > 0, "slot size is not divisible by the block size");
   nim_assert(slotIdx >= 0 && slotIdx < nslots, "slot index out of range");
 
-  // every slot is committed exactly once (the reference rebuilds the sampled slot per sample, :57; same trees)
-  std::vector<Root> slotRoots((size_t)nslots);
-  SlotHandle ours;
+  // Every slot is committed exactly once (the reference rebuilds the sampled slot per sample, :57; same trees), by ONE
+  // library call: cdx_dataset_commit deals the slots to the GPUs, batches the small ones, shards the huge ones, combines
+  // the roots and builds the dataset tree (:41-51).  Slot sources as slotCfgFromDataSetCfg gives them (dataset.nim:45-51).
+  std::vector<SlotConfig> slotCfgs;
+  std::vector<cdx_slot_desc> descs((size_t)nslots);
+  for (SlotIdx i = 0; i < nslots; ++i) slotCfgs.push_back(slotCfgFromDataSetCfg(dsetCfg, i));
   for (SlotIdx i = 0; i < nslots; ++i) {
-    SlotHandle tmp;
-    SlotHandle& dst = i == slotIdx ? ours : tmp;
-    commitSlot(be, globCfg, slotCfgFromDataSetCfg(dsetCfg, i), dst);
-    be.check(cdx_slot_root(dst.h, slotRoots[(size_t)i].data()), "treeRoot");
+    cdx_slot_desc& d = descs[(size_t)i];
+    std::memset(&d, 0, sizeof d);
+    d.n_bytes = (uint64_t)(globCfg.cellSize * ncells);
+    if (slotCfgs[(size_t)i].dataSrc.kind == DataSourceKind::FakeData) {
+      d.kind = CDX_SRC_FAKE;
+      d.seed = slotCfgs[(size_t)i].dataSrc.seed;
+    } else {
+      d.kind = CDX_SRC_FILE;                 // pread -> pinned buffers -> H2D -> sponge, overlapped (short files read as zeros, slot.nim:64-65)
+      d.path = slotCfgs[(size_t)i].dataSrc.filename.c_str();
+    }
   }
-  const SlotConfig ourSlotCfg = slotCfgFromDataSetCfg(dsetCfg, slotIdx);
+  DatasetHandles h(be);
+  const uint64_t totalBytes = (uint64_t)nslots * descs[0].n_bytes;
+  const bool useGroup = totalBytes >= ((uint64_t)1 << 30) && be.visibleGpus() > 1;
+  if (useGroup) {
+    h.group = be.group();
+    h.ds.assign((size_t)cdx_group_size(h.group), nullptr);
+    const int rc = cdx_group_dataset_commit(h.group, descs.data(), descs.size(), (size_t)globCfg.cellSize, (size_t)globCfg.blockSize, slotIdx, h.ds.data());
+    if (rc != CDX_OK) throw AssertionDefect(std::string("buildSlotTree (all GPUs): ") + cdx_group_last_error(h.group) + " [" + cdx_status_string(rc) + "]");
+  } else {
+    h.ds.assign(1, nullptr);
+    be.check(cdx_dataset_commit(be.ctx(), nullptr, descs.data(), descs.size(), (size_t)globCfg.cellSize, (size_t)globCfg.blockSize, slotIdx, &h.ds[0]),
+             "buildSlotTree");
+  }
+  cdx_dataset* ds0 = h.ds[0];
+  std::vector<Root> slotRoots((size_t)nslots);
+  be.check(cdx_dataset_slot_roots(ds0, slotRoots[0].data()), "treeRoot");
   const Root ourSlotRoot = slotRoots[(size_t)slotIdx];
+  Hash dsetRoot{};
+  be.check(cdx_dataset_root(ds0, dsetRoot.data()), "treeRoot (dataset)");                // :49-50
+  nim_assert(nslots == 1 || ceilingLog2(nslots) <= globCfg.maxLog2NSlots, "padMerkleProof: the path is longer than the requested length");
+  MerkleProof slotProof;                                                                 // :51, already padded (types.nim:27-37)
+  slotProof.leafIndex = slotIdx;
+  slotProof.leafValue = ourSlotRoot;
+  slotProof.numberOfLeaves = nslots;
+  slotProof.merklePath.assign((size_t)globCfg.maxLog2NSlots, F{});
+  {
+    const int rc = cdx_dataset_slot_proof(ds0, (uint64_t)slotIdx, (size_t)globCfg.maxLog2NSlots, slotProof.merklePath.empty() ? nullptr : slotProof.merklePath[0].data());
+    if (rc == CDX_ERR_RANGE) throw AssertionDefect("padMerkleProof: the path is longer than the requested length");
+    be.check(rc, "merkleProof (dataset)");
+  }
 
-  const MerkleTree dsetTree = merkleTree(be, hashCfg, slotRoots);                       // :49
-  const Hash dsetRoot = treeRoot(dsetTree);
-  const MerkleProof slotProof = merkleProof(dsetTree, slotIdx);
-
-  const std::vector<int64_t> indices = cellIndices(be, hashCfg, entropy, ourSlotRoot, ncells, dsetCfg.nSamples);   // :53
-
-  uint64_t nc = 0, nb = 0;
-  uint32_t bd = 0, sd = 0;
-  be.check(cdx_slot_shape(ours.h, &nc, &nb, &bd, &sd), "slot shape");
+  // sampled indices (:53), cell hashes and merged, padded paths (:56-63) in one call; the kept slot may live on any GPU
+  const int lg = ceilingLog2(ncells);
+  nim_assert(lg >= 0 && ((int64_t)1 << lg) == ncells, "for this version, `numberOfCells` is assumed to be a power of two");
+  const uint32_t bd = cpb == 1 ? 1 : (uint32_t)exactLog2(cpb);
+  const uint32_t sd = nblocks == 1 ? 1 : (uint32_t)ceilingLog2(nblocks);
   nim_assert((int)(bd + sd) <= globCfg.maxDepth, "padMerkleProof: the path is longer than the requested length");
-  const size_t ns = indices.size();
-  std::vector<uint64_t> idx64(indices.begin(), indices.end());
+  const size_t ns = (size_t)std::max<int64_t>(dsetCfg.nSamples, 0);
+  std::vector<uint64_t> idx64(ns);
   std::vector<F> paths(ns * (size_t)globCfg.maxDepth), leaves(ns);
-  if (ns) be.check(cdx_slot_cell_paths(ours.h, idx64.data(), ns, (size_t)globCfg.maxDepth, paths[0].data(), leaves[0].data()), "merkleProof (batched)");
+  if (ns) {
+    if (useGroup) {
+      const int rc = cdx_group_dataset_prove(h.group, h.ds.data(), entropy.data(), ns, (size_t)globCfg.maxDepth, idx64.data(), paths[0].data(), leaves[0].data());
+      if (rc != CDX_OK) throw AssertionDefect(std::string("merkleProof (all GPUs): ") + cdx_group_last_error(h.group) + " [" + cdx_status_string(rc) + "]");
+    } else {
+      be.check(cdx_dataset_prove(ds0, entropy.data(), ns, (size_t)globCfg.maxDepth, idx64.data(), paths[0].data(), leaves[0].data()), "merkleProof (batched)");
+    }
+  }
+  const std::vector<int64_t> indices(idx64.begin(), idx64.end());
 
-  // mergeMerkleProofs (merkle.nim:86-100) re-hashes every bottom proof and asserts it lands on the top proof's leaf;
-  // here that check runs for all samples in ONE batched verifier launch instead of 5 compressions per sample
+  // mergeMerkleProofs (merkle.nim:86-100) re-hashes every bottom proof and asserts it lands on the top proof's leaf (the
+  // block hash held in the slot tree); here that check runs for all samples in ONE batched verifier launch
   std::vector<F> botRoots(ns);
   std::vector<uint64_t> botIdx(ns);
   for (size_t s = 0; s < ns; ++s) botIdx[s] = (uint64_t)(indices[s] % cpb);
   if (ns) be.check(cdx_reconstruct_roots_host(be.ctx(), leaves[0].data(), botIdx.data(), (uint64_t)cpb, paths[0].data(), (size_t)globCfg.maxDepth,
                                               bd, ns, botRoots[0].data()), "reconstructRoot (batched)");
+  auto blockHashOf = [&](int64_t blockIdx) {            // layers[0][blockIdx] of the kept slot tree, from whichever GPU holds it
+    F out{};
+    for (cdx_dataset* d : h.ds) {
+      cdx_slot* kept = cdx_dataset_kept_slot(d);
+      if (kept && cdx_slot_read_layer(kept, 1, 0, (uint64_t)blockIdx, 1, out.data()) == CDX_OK) return out;
+    }
+    throw AssertionDefect("block hash " + std::to_string(blockIdx) + " of the sampled slot is not held by any GPU");
+  };
   SlotProofInput out;
+  const SlotConfig& ourSlotCfg = slotCfgs[(size_t)slotIdx];
   for (size_t s = 0; s < ns; ++s) {
     const int64_t cellIdx = indices[s], blockIdx = cellIdx / cpb;
     const F* p = &paths[s * (size_t)globCfg.maxDepth];
-    F blockHash{};
-    be.check(cdx_slot_read_layer(ours.h, 1, 0, (uint64_t)blockIdx, 1, blockHash.data()), "block hash");
-    nim_assert(botRoots[s] == blockHash, "mergeMerkleProofs: bottom root does not match the top leaf");
+    nim_assert(botRoots[s] == blockHashOf(blockIdx), "mergeMerkleProofs: bottom root does not match the top leaf");
     MerkleProof merged;                                                                  // merkle.nim:91-99
     merged.leafIndex = blockIdx * cpb + cellIdx % cpb;
     merged.leafValue = leaves[s];
@@ -428,7 +493,7 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
   out.nSlots = nslots;
   out.slotIndex = slotIdx;
   out.slotRoot = ourSlotRoot;
-  out.slotProof = padMerkleProof(slotProof, globCfg.maxLog2NSlots);
+  out.slotProof = slotProof;
   return out;
 }
 

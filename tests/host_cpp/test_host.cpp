@@ -1,8 +1,10 @@
 // Unit tests of the C++ host mirror of reference/nim/proof_input (host/proof_input.hpp) over the CUDA backend.
 // Built and run by tests/test_gpu_host_cpp.py on a GPU box; every hash below is computed by libcodexcommit.so.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../codex-storage-proofs-circuits_b200/host/proof_input.hpp"
@@ -127,6 +129,94 @@ int main() {
     }
     const std::string js = proofInputToJson(in);
     CHECK(js.rfind("{\n  \"dataSetRoot\":      \"", 0) == 0 && js.find(", \"nSlotsPerDataSet\": 3\n") != std::string::npos);
+  }
+  // ---- every GPU of the box through the C ABI alone (on a one-GPU box the same calls run with one rank, without NCCL) ----
+  {
+    const int nGpus = be.visibleGpus();
+    std::printf("visible GPUs: %d\n", nGpus);
+    // a 40 MiB + 3 blocks slot of counter bytes in host memory; whole-slot commitment on GPU 0 is the expectation
+    const size_t nBlocks = 643, nBytes = nBlocks * 65536;
+    std::vector<uint8_t> slot(nBytes);
+    uint64_t x = 88172645463325252ull;
+    for (size_t i = 0; i < nBytes; i += 8) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+      std::memcpy(&slot[i], &x, 8);
+    }
+    cdx_slot* whole = nullptr;
+    be.check(cdx_slot_commit_host(be.ctx(), slot.data(), nBytes, 2048, 65536, &whole), "whole");
+    F wholeRoot{};
+    be.check(cdx_slot_root(whole, wholeRoot.data()), "root");
+    const std::vector<uint64_t> cells = {0, 31, 32 * 321 + 5, 32 * nBlocks - 1};
+    std::vector<F> wantPaths(cells.size() * 32), wantLeaves(cells.size());
+    be.check(cdx_slot_cell_paths(whole, cells.data(), cells.size(), 32, wantPaths[0].data(), wantLeaves[0].data()), "paths");
+
+    // (a) one thread per GPU, each with its own context and communicator rank, cdx_slot_commit_sharded_host
+    {
+      uint8_t id[CDX_COMM_ID_BYTES] = {0};
+      if (nGpus > 1) CHECK(cdx_comm_unique_id(id) == CDX_OK);
+      std::vector<uint64_t> first(nGpus), count(nGpus);
+      int T = 0;
+      CHECK(cdx_plan_block_ranges(nBlocks, nGpus, &T, first.data(), count.data()) == CDX_OK);
+      std::vector<F> roots(nGpus), gotPaths(cells.size() * 32), gotLeaves(cells.size());
+      std::vector<int> rcs(nGpus, -100);
+      std::vector<std::thread> thr;
+      for (int r = 0; r < nGpus; ++r)
+        thr.emplace_back([&, r]() {
+          cdx_ctx* c = nullptr;
+          cdx_comm* comm = nullptr;
+          cdx_slot* sh = nullptr;
+          int rc = cdx_ctx_create(r, &c);
+          if (rc == CDX_OK) rc = cdx_comm_init_rank(c, nGpus, r, id, &comm);
+          if (rc == CDX_OK)
+            rc = cdx_slot_commit_sharded_host(c, comm, count[r] ? slot.data() + first[r] * 65536 : nullptr, count[r] * 65536, 2048, 65536, first[r],
+                                              nBlocks, T, &sh);
+          if (rc == CDX_OK) rc = cdx_slot_root(sh, roots[r].data());
+          std::vector<F> p(cells.size() * 32), l(cells.size());
+          if (rc == CDX_OK) rc = cdx_slot_cell_paths_sharded(sh, comm, cells.data(), cells.size(), 32, p[0].data(), l[0].data());
+          if (rc == CDX_OK && r == nGpus - 1) { gotPaths = p; gotLeaves = l; }
+          if (rc != CDX_OK) std::printf("rank %d: %s\n", r, cdx_last_error(c));
+          cdx_slot_free(sh);
+          cdx_comm_destroy(comm);
+          cdx_ctx_destroy(c);
+          rcs[r] = rc;
+        });
+      for (auto& t : thr) t.join();
+      for (int r = 0; r < nGpus; ++r) CHECK(rcs[r] == CDX_OK && roots[r] == wholeRoot);
+      CHECK(gotPaths == wantPaths && gotLeaves == wantLeaves);
+    }
+    // (b) the same through the group entry points
+    {
+      cdx_group* grp = be.group();
+      CHECK(cdx_group_size(grp) == nGpus);
+      std::vector<cdx_slot*> shards(nGpus, nullptr);
+      const int rc = cdx_group_slot_commit_host(grp, slot.data(), nBytes, 2048, 65536, shards.data());
+      if (rc != CDX_OK) std::printf("group: %s\n", cdx_group_last_error(grp));
+      CHECK(rc == CDX_OK);
+      for (int r = 0; r < nGpus && rc == CDX_OK; ++r) {
+        F root{};
+        CHECK(cdx_slot_root(shards[r], root.data()) == CDX_OK && root == wholeRoot);
+      }
+      std::vector<F> p(cells.size() * 32), l(cells.size());
+      CHECK(cdx_group_slot_cell_paths(grp, shards.data(), cells.data(), cells.size(), 32, p[0].data(), l[0].data()) == CDX_OK);
+      CHECK(p == wantPaths && l == wantLeaves);
+      cdx_group_slots_free(grp, shards.data());
+    }
+    cdx_slot_free(whole);
+    // (c) generateProofInputBN254 over a dataset large enough for the all-GPU path (20 slots x 64 MiB of the reference's fake
+    //     data = 1.25 GiB) equals the same call pinned to one GPU, and the verifier accepts it
+    {
+      DataSetConfig d;
+      d.nCells = 32768;
+      d.nSlots = 20;
+      d.nSamples = 7;
+      const SlotProofInput all = generateProofInputBN254(be, h, g, d, 13, felt(424242));
+      setenv("CODEX_COMMIT_GPUS", "1", 1);
+      const SlotProofInput one = generateProofInputBN254(be, h, g, d, 13, felt(424242));
+      unsetenv("CODEX_COMMIT_GPUS");
+      CHECK(proofInputToJson(all) == proofInputToJson(one));
+      std::string why;
+      CHECK(checkProofInputBN254(be, g, all, &why));
+    }
   }
   std::printf(failures ? "%d FAILURES\n" : "host mirror: all checks passed\n", failures);
   return failures ? 1 : 0;
