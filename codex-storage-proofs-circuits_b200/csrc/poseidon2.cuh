@@ -26,6 +26,7 @@ static const Fr h_rc[80] = P2_RC_MONT_INIT;
 #define CDX_RC(i) h_rc[i]
 #endif
 
+
 // capacity IV = 2^64 + 256*t + rate (Sponge.hs:17,34) in Montgomery form: computed once per thread (2 modmuls)
 CDX_D Fr sponge_iv(int rate) {
   Fr a = fr_zero();

@@ -86,3 +86,35 @@ def test_planners_and_comm_without_a_gpu(pkg):
     lib = pkg.load_library()
     assert lib.cdx_comm_rank(None) == 0 and lib.cdx_comm_size(None) == 1
     assert lib.cdx_group_size(None) == 0 and lib.cdx_dataset_kept_slot(None) is None
+
+
+def test_nim_binding_declares_every_symbol():
+    """the Nim delivery (cannot be compiled here: no Nim toolchain) at least covers the whole ABI: the generated binding has
+    one importc per header function, and regenerating it changes nothing"""
+    import subprocess
+    import sys
+    path = os.path.join(ROOT, "codex-storage-proofs-circuits_b200", "nim", "codexcommit_abi.nim")
+    before = open(path).read()
+    declared = set(re.findall(r"^proc (cdx_[a-z0-9_]+)\*\(", before, flags=re.M))
+    assert declared == set(header_functions())
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_nim_binding.py")], check=True, capture_output=True)
+    assert open(path).read() == before
+
+
+def test_nim_patch_series_applies_to_the_reference(tmp_path):
+    """nim/patches/*.patch apply cleanly to reference/nim/proof_input/src (only checkable where /root/reference exists)"""
+    import shutil
+    import subprocess
+    ref = "/root/reference/reference/nim/proof_input"
+    if not os.path.isdir(ref) or shutil.which("patch") is None:
+        pytest.skip("the reference tree (or patch) is not available here")
+    dst = tmp_path / "reference" / "nim" / "proof_input"
+    shutil.copytree(ref, dst)
+    pdir = os.path.join(ROOT, "codex-storage-proofs-circuits_b200", "nim", "patches")
+    patches = sorted(f for f in os.listdir(pdir) if f.endswith(".patch"))
+    assert len(patches) == 4
+    for f in patches:
+        res = subprocess.run(["patch", "-p1", "--forward", "-i", os.path.join(pdir, f)], cwd=tmp_path, capture_output=True, text=True)
+        assert res.returncode == 0, f + "\n" + res.stdout + res.stderr
+    src = (dst / "src" / "gen_input" / "bn254.nim").read_text()
+    assert "cdx_group_dataset_commit" in src and "proc generateProofInputBN254*( hashCfg: HashConfig, globCfg: GlobalConfig, dsetCfg: DataSetConfig, slotIdx: SlotIdx, entropy: Entropy ): SlotProofInput[Hash]" in src

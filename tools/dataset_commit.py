@@ -40,43 +40,52 @@ def main():
         k -= 1
     blocks = dataset.draw_slot_blocks(args.nslots, args.min_gib * args.scale * gib, args.max_gib * args.scale * gib, args.seed,
                                       pow2_slot=args.sampled_slot, pow2_blocks=(1 << k) // 32)
+    sharded = importlib.import_module(PKG + ".sharded")
+    comm = sharded.comm_from_torch(ctx) if world > 1 else None       # the library's NCCL communicator; torch only carries the id
+    descs = dataset.synthetic_descs(blocks, args.seed)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = dataset.commit_dataset(ctx, blocks, args.seed, args.sampled_slot, args.entropy, args.nsamples, rank=rank, world=world)
+    ds = ctx.dataset_commit(comm, descs, keep_slot=args.sampled_slot)                      # cdx_dataset_commit: everything inside the library
+    t_commit = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    idx, paths, leaves = ds.prove(args.entropy, args.nsamples, 32)                           # cdx_dataset_prove (collective)
+    t_prove = time.perf_counter() - t1
     wall = time.perf_counter() - t0
-    # self-check on rank 0 (GPU compression only): every sampled path reconstructs to the slot root in two stages, and
+    stats = ds.stats
+    tt = torch.tensor([t_commit, t_prove, float(stats["bytes_local"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    # self-check on rank 0 (GPU verifier kernel): every sampled path reconstructs to the slot root in two stages, and
     # the slot proof reconstructs to the dataset root (merkle.nim:51-74)
-    ok = None
     if rank == 0:
-        def reconstruct(leaf, j, m, path):
-            h, bottom = leaf, 1
-            for p in path:
-                if j & 1: h = ctx.compress(p, h, bottom)
-                elif j == m - 1: h = ctx.compress(h, p, bottom + 2)
-                else: h = ctx.compress(h, p, bottom)
-                bottom, j, m = 0, j >> 1, (m + 1) >> 1
-            return h
         nb = blocks[args.sampled_slot]
         depth = max(1, (nb - 1).bit_length())
-        sroot = res.slot_roots[args.sampled_slot]
-        ok = True
-        for ci, path, leaf in list(zip(res.cell_indices, res.merkle_paths, res.cell_hashes))[:10]:
-            blk = reconstruct(leaf, ci % 32, 32, path[:5])
-            ok &= reconstruct(blk, ci // 32, nb, path[5:5 + depth]) == sroot
-        dd = len(res.dataset_layers) - 1
-        ok &= reconstruct(sroot, args.sampled_slot, args.nslots, res.slot_proof[:dd]) == res.dataset_root
-        total = res.bytes_committed
+        roots = ds.slot_roots
+        sroot = roots[args.sampled_slot]
+        blk = ctx.reconstruct_roots(leaves, [ci % 32 for ci in idx], 32, paths, depth=5)
+        top = ctx.reconstruct_roots(blk, [ci // 32 for ci in idx], nb, [p[5:] for p in paths], depth=depth)
+        ok = all(t == sroot for t in top)
+        dd = max(1, (args.nslots - 1).bit_length())
+        sp = ds.slot_proof(args.sampled_slot, 8)
+        ok &= ctx.reconstruct_roots([sroot], [args.sampled_slot], args.nslots, [sp], depth=dd)[0] == ds.root
+        total = sum(blocks) * 65536
         perms = sum(b * 1119 for b in blocks)
         line = {"workload": f"dataset of {args.nslots} synthetic slots, sizes log-uniform {args.min_gib * args.scale:g}-{args.max_gib * args.scale:g} GiB, "
-                            f"{world} GPU(s), LPT bin packing; dataset root + {args.nsamples} sampled paths of slot {args.sampled_slot}",
-                "n_gpus": world, "bytes": total, "commit_s": res.timings["commit_s"], "roots_tree_paths_s": res.timings["roots_tree_paths_s"],
-                "wall_s": wall, "GB_per_s": total / res.timings["commit_s"] / 1e9, "perms_per_s": perms / res.timings["commit_s"],
-                "balance": max(res.per_rank_bytes) / (total / world), "dataset_root": hex(res.dataset_root),
-                "dataset_tree_layers": [len(l) for l in res.dataset_layers], "sampled_slot_cells": blocks[args.sampled_slot] * 32,
-                "first_indices": res.cell_indices[:5], "paths_self_check": bool(ok)}
+                            f"{world} GPU(s); cdx_dataset_commit (LPT packing, batching, sharding inside the library) + cdx_dataset_prove: "
+                            f"dataset root + {args.nsamples} sampled paths of slot {args.sampled_slot}",
+                "n_gpus": world, "bytes": total, "commit_s": float(tt[0]), "prove_s": float(tt[1]),
+                "wall_s": wall, "GB_per_s": total / float(tt[0]) / 1e9, "perms_per_s": perms / float(tt[0]),
+                "balance": float(tt[2]) / (total / world), "dataset_root": hex(ds.root), "rank0_stats": stats,
+                "sampled_slot_cells": blocks[args.sampled_slot] * 32, "first_indices": idx[:5], "paths_self_check": bool(ok)}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
+    ds.free()
+    if comm is not None:
+        comm.destroy()
     if world > 1:
         dist.destroy_process_group()
 

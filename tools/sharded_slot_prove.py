@@ -3,7 +3,7 @@
 
 Every rank generates and commits its own 2^T-aligned block range, ONE all-gather exchanges the level-T nodes, every
 rank builds the replicated top tree; the sampled indices are derived from the root on every rank, each cell's owner
-produces its Merkle path and a uint8 SUM all-reduce delivers them (sharded.gather_cell_paths).  Rank 0 then verifies
+produces its Merkle path and a byte-wise SUM inside the library delivers them (cdx_slot_prove_batch_sharded).  Rank 0 then verifies
 every path in two stages on its GPU (block tree, slot tree -- Slot.hs:189-217) and, with --check-whole, re-commits the
 whole slot alone and compares root, paths and leaves with the sharded answer.
 
@@ -58,10 +58,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def commit():
-        sh = sharded.GpuShard(ctx.slot_commit_range_dev(d.data_ptr(), n_bytes, CELL, BLOCK, first_block, n_total_blocks, top_level))
-        sharded.exchange_subtree_roots(sh, n_total_blocks, top_level, ranges)
-        return sh
+    comm = sharded.comm_from_torch(ctx)               # the library's NCCL communicator; torch only carries the 128-byte id
+
+    def commit():                                     # range commit + exchange + top tree: one C-ABI call
+        return ctx.slot_commit_sharded_dev(comm, d.data_ptr(), n_bytes, CELL, BLOCK, first_block, n_total_blocks, top_level)
 
     commit().free()                                   # warm-up: pool allocations, NCCL channels
     barrier()
@@ -72,8 +72,7 @@ def main():
     t_commit = time.perf_counter() - t0
 
     t0 = time.perf_counter()
-    indices = ctx.cell_indices(args.entropy, root, n_cells, args.samples)      # same on every rank
-    paths, leaves = sharded.gather_cell_paths(sh, indices, 32)
+    (indices,), (paths,), (leaves,) = sh.prove_batch_sharded(comm, [args.entropy], args.samples, 32)   # cdx_slot_prove_batch_sharded
     barrier()
     t_prove = time.perf_counter() - t0
 
