@@ -371,7 +371,7 @@ def main() -> None:
         try:
             tj = json.load(open(traffic_file))
             roofline["traffic"] = tj["dram_bytes_per_slot_byte"] * n_bytes
-            roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of k_hash_cells, scaled per slot byte from the "
+            roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of k_hash_cells_tma, scaled per slot byte from the "
                                         f"{tj['slot_bytes_in_launch'] >> 30} GiB launch captured in {tj['source']}")
         except Exception:
             pass
