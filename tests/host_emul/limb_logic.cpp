@@ -17,6 +17,21 @@ void emul_mont_sqr_raw(const uint8_t* a, uint8_t* out) { store(out, mont_sqr(loa
 void emul_to_mont(const uint8_t* a, uint8_t* out) { store(out, to_mont(load(a))); }
 void emul_from_mont(const uint8_t* a, uint8_t* out) { store(out, from_mont(load(a))); }
 void emul_add_mod(const uint8_t* a, const uint8_t* b, uint8_t* out) { store(out, add_mod(load(a), load(b))); }
+// table-driven reduction and the mixes built on it, on RAW limb values (no conversion): the tests drive them at the
+// edges of their documented input ranges; the emulated primitives trap on any violated bound
+void emul_reduce_tab(const uint8_t* v, uint32_t carry, uint8_t* out) { store(out, reduce_tab(load(v), carry)); }
+void emul_add_reduce(const uint8_t* a, const uint8_t* b, uint8_t* out) { store(out, add_reduce(load(a), load(b))); }
+void emul_mix_internal_raw(uint8_t* x, uint8_t* y, uint8_t* z) {
+  Fr a = load(x), b = load(y), c = load(z);
+  mix_internal(a, b, c);
+  store(x, a); store(y, b); store(z, c);
+}
+void emul_mix_external_raw(uint8_t* x, uint8_t* y, uint8_t* z) {
+  Fr a = load(x), b = load(y), c = load(z);
+  mix_external(a, b, c);
+  store(x, a); store(y, b); store(z, c);
+}
+void emul_sbox_raw(const uint8_t* x, uint8_t* out) { store(out, sbox(load(x))); }
 void emul_permutation(const uint8_t* in, uint8_t* out) {
   Fr x = to_mont(load(in)), y = to_mont(load(in + 32)), z = to_mont(load(in + 64));
   permute(x, y, z);

@@ -65,6 +65,54 @@ def test_mont_sqr_dedicated(emul):
         assert v % R == a * a * rinv % R and v <= (a * a >> 256) + R
 
 
+def test_table_reduction_and_mixes_at_their_bounds(emul):
+    """reduce_tab maps any v < 2^257 to the congruent value below B = r + 2^250; the S-box and both mixes keep their
+    documented ranges when driven at the edges (state words B - 1, S-box results 1.64 r): the emulation traps on any carry
+    out of a lazy add and on any reduction result >= B, so finishing is the check; values are compared mod r"""
+    rnd = random.Random(23)
+    B = R + (1 << 250)
+    out = C.create_string_buffer(32)
+    vals = [0, 1, R - 1, R, R + 1, B - 1, B, 2 * R, 5 * R, (1 << 256) - 1] + [rnd.randrange(1 << 256) for _ in range(3000)]
+    vals += [k << 250 for k in range(64)] + [(k << 250) - 1 for k in range(1, 65)]
+    for v in vals:
+        emul.emul_reduce_tab(f2b(v), 0, out)
+        w = b2f(out.raw)
+        assert w % R == v % R and w < B, hex(v)
+    for v in vals + [(1 << 256) - 1]:                      # with the carry: the value is v + 2^256
+        emul.emul_reduce_tab(f2b(v), 1, out)
+        w = b2f(out.raw)
+        assert w % R == (v + (1 << 256)) % R and w < B, hex(v)
+    for a, b in [(B - 1, (1 << 256) - 1), ((1 << 256) - 1, (1 << 256) - 1), (0, 0), (R, B)] + [(rnd.randrange(1 << 256), rnd.randrange(1 << 256)) for _ in range(500)]:
+        emul.emul_add_reduce(f2b(a), f2b(b), out)
+        w = b2f(out.raw)
+        assert w % R == (a + b) % R and w < B
+    rinv5 = pow(1 << 256, -4, R)                               # sbox on raw values: x^5 R^-4
+    sbox_in_max = ((1 << 256) - R) // 2 - 1                    # mont_sqr's window bound, 2.14 r
+    for x in [0, 1, B - 1, B + R - 1, 2 * R, sbox_in_max] + [rnd.randrange(B + R) for _ in range(300)]:
+        emul.emul_sbox_raw(f2b(x), out)
+        w = b2f(out.raw)
+        assert w % R == pow(x, 5, R) * rinv5 % R
+        if x < B + R:
+            assert w < 164 * R // 100                          # the documented 1.64 r
+    sb_max = 164 * R // 100
+    bx, by, bz = (C.create_string_buffer(32) for _ in range(3))
+    cases = [(sb_max, B - 1, B - 1), (sb_max, 0, 0), (0, B - 1, B - 1), (0, 0, 0)] + [(rnd.randrange(sb_max), rnd.randrange(B), rnd.randrange(B)) for _ in range(500)]
+    for x, y, z in cases:
+        for buf, v in ((bx, x), (by, y), (bz, z)):
+            buf.raw = f2b(v)
+        emul.emul_mix_internal_raw(bx, by, bz)
+        s = x + y + z
+        got = [b2f(b.raw) for b in (bx, by, bz)]
+        assert [g % R for g in got] == [(x + s) % R, (y + s) % R, (2 * z + s) % R] and all(g < B for g in got)
+    for x, y, z in [(sb_max, sb_max, sb_max), (0, 0, 0), (B - 1, B - 1, B - 1)] + [tuple(rnd.randrange(sb_max) for _ in range(3)) for _ in range(500)]:
+        for buf, v in ((bx, x), (by, y), (bz, z)):
+            buf.raw = f2b(v)
+        emul.emul_mix_external_raw(bx, by, bz)
+        s = x + y + z
+        got = [b2f(b.raw) for b in (bx, by, bz)]
+        assert [g % R for g in got] == [(x + s) % R, (y + s) % R, (z + s) % R] and all(g < B for g in got)
+
+
 def test_permutation_and_compress(emul, orc):
     rnd = random.Random(8)
     out = C.create_string_buffer(96)
