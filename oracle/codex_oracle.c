@@ -38,11 +38,25 @@ static inline void fr_sub_mod_inplace(uint64_t a[4]) {
   }
 }
 
+/* [0, 2r) -> [0, r) without a data-dependent branch (the comparison is a coin flip on this path: a mispredicted branch
+ * per addition would cost more than the addition): trial subtraction, then select by the borrow */
+static inline void fr_reduce_once(uint64_t a[4]) {
+  uint64_t d[4];
+  u128 b = 0;
+  for (int i = 0; i < 4; ++i) {
+    u128 t = (u128)a[i] - FR_MOD[i] - (uint64_t)b;
+    d[i] = (uint64_t)t;
+    b = (t >> 64) & 1;
+  }
+  const uint64_t keep = (uint64_t)0 - (uint64_t)b;      /* all ones if a < r */
+  for (int i = 0; i < 4; ++i) a[i] = (a[i] & keep) | (d[i] & ~keep);
+}
+
 static inline fr fr_add(fr a, fr b) {
   fr c; u128 cy = 0;
   for (int i = 0; i < 4; ++i) { cy += (u128)a.l[i] + b.l[i]; c.l[i] = (uint64_t)cy; cy >>= 64; }
   /* r < 2^254 so a+b < 2^255: no carry out of limb 3 */
-  if (fr_geq_mod(c.l)) fr_sub_mod_inplace(c.l);
+  fr_reduce_once(c.l);
   return c;
 }
 
@@ -52,7 +66,7 @@ static inline fr fr_dbl(fr a) { return fr_add(a, a); }
  * multiply and reduce rows interleaved; because r < 2^254 the running value never needs a fifth limb
  * (the usual simplification for moduli with spare top bits). */
 #define MAC(hi, lo, x, y, add1, add2) do { u128 _p = (u128)(x) * (y) + (add1) + (add2); lo = (uint64_t)_p; hi = (uint64_t)(_p >> 64); } while (0)
-static inline fr fr_mul(fr a, fr b) {
+static inline fr fr_mul_c(fr a, fr b) {
   uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 #define ROW(bi) do {                                         \
     uint64_t A, Cc, m, lo;                                   \
@@ -70,9 +84,54 @@ static inline fr fr_mul(fr a, fr b) {
   ROW(b.l[0]); ROW(b.l[1]); ROW(b.l[2]); ROW(b.l[3]);
 #undef ROW
   fr r = {{t0, t1, t2, t3}};
-  if (fr_geq_mod(r.l)) fr_sub_mod_inplace(r.l);
+  fr_reduce_once(r.l);
   return r;
 }
+
+
+#if defined(__x86_64__) && defined(__BMI2__) && defined(__ADX__) && !defined(ORC_NO_ASM)
+/* The same word-serial product with the instructions tuned field libraries use on x86-64 (constantine, the reference's
+ * arithmetic backend, among them): MULX for the 64x64->128 products and the two independent carry chains of ADCX (CF) and
+ * ADOX (OF), so the low and the high halves of a row accumulate in parallel.  Per row: t += a*b_i (t4 = the word above),
+ * m = t0 * (-r^-1), t = (t + m*r) / 2^64.  The five accumulator registers rotate instead of being shifted.  r < 2^254
+ * keeps t4 within one word (the "no-carry" form).  Built only where the compiler targets BMI2+ADX; fr_mul_c is the
+ * portable statement of the same function and the unit tests compare the two. */
+#define ORC_ROW(T0, T1, T2, T3, T4, OFF)                                          \
+  "xorl %%eax, %%eax\n\t"                                                        \
+  "movq " #OFF "(%[b]), %%rdx\n\t"                                               \
+  "mulx 0(%[a]), %%r13, %%r14\n\t"   "adox %%r13, " T0 "\n\t"                    \
+  "mulx 8(%[a]), %%r13, %%r15\n\t"   "adcx %%r14, " T1 "\n\t" "adox %%r13, " T1 "\n\t" \
+  "mulx 16(%[a]), %%r13, %%r14\n\t"  "adcx %%r15, " T2 "\n\t" "adox %%r13, " T2 "\n\t" \
+  "mulx 24(%[a]), %%r13, %%r15\n\t"  "adcx %%r14, " T3 "\n\t" "adox %%r13, " T3 "\n\t" \
+  "movl $0, %%r13d\n\t"              "movq %%r13, " T4 "\n\t"                    \
+  "adcx %%r15, " T4 "\n\t"           "adox %%rax, " T4 "\n\t"                    \
+  "movq " T0 ", %%rdx\n\t"           "imulq %[ninv], %%rdx\n\t"                  \
+  "xorl %%eax, %%eax\n\t"                                                        \
+  "mulx 0(%[q]), %%r13, %%r14\n\t"   "adox " T0 ", %%r13\n\t"                    \
+  "mulx 8(%[q]), %%r13, %%r15\n\t"   "adcx %%r14, " T1 "\n\t" "adox %%r13, " T1 "\n\t" \
+  "mulx 16(%[q]), %%r13, %%r14\n\t"  "adcx %%r15, " T2 "\n\t" "adox %%r13, " T2 "\n\t" \
+  "mulx 24(%[q]), %%r13, %%r15\n\t"  "adcx %%r14, " T3 "\n\t" "adox %%r13, " T3 "\n\t" \
+  "adcx %%r15, " T4 "\n\t"           "adox %%rax, " T4 "\n\t"
+static inline fr fr_mul(fr a, fr b) {
+  fr r;
+  __asm__ volatile(
+      "xorl %%r8d, %%r8d\n\t" "xorl %%r9d, %%r9d\n\t" "xorl %%r10d, %%r10d\n\t" "xorl %%r11d, %%r11d\n\t"
+      ORC_ROW("%%r8", "%%r9", "%%r10", "%%r11", "%%r12", 0)
+      ORC_ROW("%%r9", "%%r10", "%%r11", "%%r12", "%%r8", 8)
+      ORC_ROW("%%r10", "%%r11", "%%r12", "%%r8", "%%r9", 16)
+      ORC_ROW("%%r11", "%%r12", "%%r8", "%%r9", "%%r10", 24)
+      "movq %%r12, 0(%[r])\n\t" "movq %%r8, 8(%[r])\n\t" "movq %%r9, 16(%[r])\n\t" "movq %%r10, 24(%[r])\n\t"
+      :
+      : [a] "r"(a.l), [b] "r"(b.l), [q] "r"(FR_MOD), [ninv] "m"(FR_NINV), [r] "r"(r.l)
+      : "rax", "rdx", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15", "cc", "memory");
+  fr_reduce_once(r.l);
+  return r;
+}
+#define ORC_HAVE_ASM 1
+#else
+static inline fr fr_mul(fr a, fr b) { return fr_mul_c(a, b); }
+#define ORC_HAVE_ASM 0
+#endif
 
 /* Montgomery square a*a*2^-256 mod r: the 6 cross products once, doubled, plus the 4 squares (10 multiplications instead
  * of 16), then a separate 4-row Montgomery reduction of the 512-bit product -- what constantine and every tuned field
@@ -102,16 +161,18 @@ static inline fr fr_sqr(fr a) {
   p = (u128)t[5] + c;                        t[5] = (uint64_t)p; c = (uint64_t)(p >> 64);
   p = (u128)a.l[3] * a.l[3] + t[6] + c;      t[6] = (uint64_t)p; c = (uint64_t)(p >> 64);
   t[7] += c;
+  uint64_t up = 0;                             /* carry into the limb above the current row */
   for (int i = 0; i < 4; ++i) {              /* row i clears limb i */
     const uint64_t m = t[i] * FR_NINV;
     p = (u128)m * FR_MOD[0] + t[i];          c = (uint64_t)(p >> 64);
     p = (u128)m * FR_MOD[1] + t[i + 1] + c;  t[i + 1] = (uint64_t)p; c = (uint64_t)(p >> 64);
     p = (u128)m * FR_MOD[2] + t[i + 2] + c;  t[i + 2] = (uint64_t)p; c = (uint64_t)(p >> 64);
     p = (u128)m * FR_MOD[3] + t[i + 3] + c;  t[i + 3] = (uint64_t)p; c = (uint64_t)(p >> 64);
-    for (int k = i + 4; k < 8 && c; ++k) { p = (u128)t[k] + c; t[k] = (uint64_t)p; c = (uint64_t)(p >> 64); }
+    p = (u128)t[i + 4] + c + up;             t[i + 4] = (uint64_t)p; up = (uint64_t)(p >> 64);
   }
+  /* up == 0 here: a^2 + sum m_i r 2^(64 i) < 2^512 */
   fr r = {{t[4], t[5], t[6], t[7]}};
-  if (fr_geq_mod(r.l)) fr_sub_mod_inplace(r.l);
+  fr_reduce_once(r.l);
   return r;
 }
 
@@ -151,8 +212,15 @@ static inline void ensure_init(void) { pthread_once(&g_once, init_tables); }
 /* ---------------------------------------------------------------------------------------------------------- */
 /* Poseidon2                                       reference/haskell/src/Poseidon2/Permutation.hs:14-45 */
 
+static int g_use_sqr = 1;   /* bench.py's CPU legs time both forms on the host they run on and keep the faster one */
+void orc_set_use_sqr(int on) { g_use_sqr = on; }
+
 static inline fr sbox(fr x) {                       /* Permutation.hs:14-17 */
-  fr x2 = fr_sqr(x), x4 = fr_sqr(x2);
+  if (g_use_sqr) {
+    fr x2 = fr_sqr(x), x4 = fr_sqr(x2);
+    return fr_mul(x4, x);
+  }
+  fr x2 = fr_mul(x, x), x4 = fr_mul(x2, x2);
   return fr_mul(x4, x);
 }
 
@@ -189,7 +257,14 @@ void orc_permutation(const uint8_t in[96], uint8_t out[96]) {
   for (int j = 0; j < 3; ++j) fr_to_bytes(s[j], out + 32 * j);
 }
 
-/* unit-test hook: a^2 through the dedicated squaring and through the general product (both canonical) */
+/* unit-test hooks */
+int orc_have_asm(void) { return ORC_HAVE_ASM; }
+void orc_fr_mul_check(const uint8_t a[32], const uint8_t b[32], uint8_t out_fast[32], uint8_t out_c[32]) {
+  fr x = fr_from_bytes(a), y = fr_from_bytes(b);
+  fr_to_bytes(fr_mul(x, y), out_fast);
+  fr_to_bytes(fr_mul_c(x, y), out_c);
+}
+/* a^2 through the dedicated squaring and through the general product (both canonical) */
 void orc_fr_sqr_check(const uint8_t a[32], uint8_t out_sqr[32], uint8_t out_mul[32]) {
   fr x = fr_from_bytes(a);
   fr_to_bytes(fr_sqr(x), out_sqr);

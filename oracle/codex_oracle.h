@@ -21,6 +21,11 @@ extern "C" {
 /* Poseidon2 t=3 permutation                       reference/haskell/src/Poseidon2/Permutation.hs:40-45 */
 void orc_permutation(const uint8_t in[96], uint8_t out[96]);
 void orc_permutation_batch(const uint8_t *in, uint8_t *out, size_t n);
+/* 1 if the MULX/ADCX/ADOX product was compiled in; a*b mod r (standard form in and out) through it and through the portable C product */
+int orc_have_asm(void);
+void orc_fr_mul_check(const uint8_t a[32], const uint8_t b[32], uint8_t out_fast[32], uint8_t out_c[32]);
+/* x^2 and x^4 of the S-box through the dedicated squaring (1, default) or the general product (0): same results */
+void orc_set_use_sqr(int on);
 /* unit-test hook: a^2 mod r (standard form in and out) through fr_sqr and through fr_mul(a, a) */
 void orc_fr_sqr_check(const uint8_t a[32], uint8_t out_sqr[32], uint8_t out_mul[32]);
 

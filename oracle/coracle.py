@@ -61,6 +61,7 @@ def lib():
             build()
         L = C.CDLL(_SO)
         L.orc_fr_sqr_check.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+        L.orc_fr_mul_check.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
         u8p, sz, u64 = C.c_char_p, C.c_size_t, C.c_uint64
         L.orc_permutation.argtypes = [u8p, u8p]
         L.orc_permutation_batch.argtypes = [u8p, u8p, sz]
@@ -98,6 +99,22 @@ def pack(xs: Sequence[int]) -> bytes:
 
 def unpack(buf: bytes) -> List[int]:
     return [int.from_bytes(buf[i:i + 32], "little") for i in range(0, len(buf), 32)]
+
+
+def set_use_sqr(on: bool) -> None:
+    """S-box squarings through the dedicated 10-product squaring (default) or the general CIOS product; identical results"""
+    lib().orc_set_use_sqr(1 if on else 0)
+
+
+def have_asm() -> bool:
+    return bool(lib().orc_have_asm())
+
+
+def fr_mul_check(a: int, b: int) -> Tuple[int, int]:
+    """(a*b mod r via the build's fast product -- MULX/ADCX/ADOX where compiled in --, via the portable C product)"""
+    o1, o2 = C.create_string_buffer(32), C.create_string_buffer(32)
+    lib().orc_fr_mul_check(f2b(a), f2b(b), o1, o2)
+    return b2f(o1.raw), b2f(o2.raw)
 
 
 def fr_sqr_check(a: int) -> Tuple[int, int]:

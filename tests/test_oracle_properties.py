@@ -65,3 +65,17 @@ def test_oracle_dedicated_squaring(orc):
     for a in cases:
         s, m = orc.fr_sqr_check(a)
         assert s == m == a * a % R, hex(a)
+
+
+def test_oracle_adx_product_equals_portable_product(orc):
+    """the MULX/ADCX/ADOX Montgomery product (compiled in where the target has BMI2+ADX) against the portable C product
+    and a*b mod r"""
+    import random
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    rnd = random.Random(4)
+    edge = [0, 1, 2, R - 1, R - 2, (1 << 64) - 1, (1 << 128) - 1, (1 << 192) - 1, 1 << 253, (1 << 254) % R, 0xffffffffffffffff << 64,
+            0xffffffffffffffff << 128, 0xffffffffffffffff << 192 & (R - 1)]
+    cases = [(a, b) for a in edge for b in edge] + [(rnd.randrange(R), rnd.randrange(R)) for _ in range(5000)]
+    for a, b in cases:
+        fast, c = orc.fr_mul_check(a, b)
+        assert fast == c == a * b % R, (hex(a), hex(b))
