@@ -318,6 +318,55 @@ def test_paths_errors(ctx, pkg):
 
 # ---- error behaviour (the reference asserts; the ABI returns status codes) -----------------------------------
 
+def test_multi_gpu_and_dataset_entry_point_errors(ctx, pkg):
+    """status codes of the round-2 entry points: every misuse is an error return with a message, never a crash"""
+    E, capi = pkg.CodexCommitError, pkg.capi
+    small = 2 * 65536
+    with pytest.raises(E) as e:
+        ctx.dataset_commit(None, [(capi.SRC_SYNTHETIC, 1, small)], keep_slot=1)        # keep_slot outside the dataset
+    assert e.value.status == capi.CDX_ERR_RANGE
+    with pytest.raises(E) as e:
+        ctx.dataset_commit(None, [(capi.SRC_SYNTHETIC, 1, small + 100)])                 # not a whole number of blocks
+    assert e.value.status == capi.CDX_ERR_SIZE
+    with pytest.raises(E) as e:
+        ctx.dataset_commit(None, [(7, 1, small)])                                        # unknown source kind
+    assert e.value.status == capi.CDX_ERR_ARG
+    with ctx.dataset_commit(None, [(capi.SRC_SYNTHETIC, 1, small), (capi.SRC_FAKE, 2, 3 * 65536)], keep_slot=1) as ds:
+        with pytest.raises(E) as e:
+            ds.prove(5, 4, 32)                                                           # 96 cells: not a power of two (sample/bn254.nim:19-20)
+        assert e.value.status == capi.CDX_ERR_NOT_POW2
+        with pytest.raises(E) as e:
+            ds.slot_proof(2, 8)                                                          # slot index out of range
+        assert e.value.status == capi.CDX_ERR_RANGE
+        with pytest.raises(E) as e:
+            ds.slot_proof(0, 0)                                                          # padMerkleProof: depth too small (types.nim:29)
+        assert e.value.status == capi.CDX_ERR_RANGE
+    with ctx.dataset_commit(None, [(capi.SRC_SYNTHETIC, 1, small)]) as ds:               # nothing kept
+        with pytest.raises(E) as e:
+            ds.prove(5, 4, 32)
+        assert e.value.status == capi.CDX_ERR_STATE
+    with pytest.raises(E) as e:
+        ctx.comm_init(2, 2, b"\0" * 128)                                                 # rank outside 0..n-1
+    assert e.value.status == capi.CDX_ERR_ARG
+    with pytest.raises(E) as e:
+        ctx.comm_init(2, 0, None)                                                        # several ranks need the id
+    assert e.value.status == capi.CDX_ERR_STATE
+    comm = ctx.comm_init(1, 0, None)
+    d = bytes(8 * 65536)
+    with pytest.raises(E) as e:
+        ctx.slot_commit_sharded_host(comm, d, len(d), 2048, 65536, 3, 64, 2)            # first block not aligned to 2^top_level
+    assert e.value.status == capi.CDX_ERR_SIZE
+    with pytest.raises(E) as e:
+        ctx.slot_commit_sharded_host(comm, d, len(d), 2048, 65536, 60, 64, 0)           # range runs past the end of the slot
+    assert e.value.status == capi.CDX_ERR_RANGE
+    with pytest.raises(E) as e:
+        ctx.slots_commit_batch_host(d, [65536, 0])                                       # an empty slot in a batch
+    assert e.value.status == capi.CDX_ERR_SIZE
+    with pytest.raises(E):
+        capi.plan_block_ranges(0, 4)
+    comm.destroy()
+
+
 def test_size_and_power_of_two_errors(ctx, pkg):
     E = pkg.CodexCommitError
     with pytest.raises(E) as e:
