@@ -21,6 +21,7 @@ _vp, _u8p, _sz, _u64, _u32, _int = C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint6
 _pp = C.POINTER(C.c_void_p)
 SYMBOLS = {
     "cdx_abi_version": (_int, []),
+    "cdx_device_count": (_int, []),
     "cdx_ctx_create": (_int, [_int, _pp]),
     "cdx_ctx_destroy": (None, [_vp]),
     "cdx_last_error": (C.c_char_p, [_vp]),

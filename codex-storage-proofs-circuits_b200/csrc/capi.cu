@@ -42,6 +42,7 @@ struct cdx_ctx {
   int stage_count = 0;
   int stage_tiles = 3;                 // tiles in flight for pinned host slots (CODEX_COMMIT_STAGE_TILES = 2..4)
   size_t tile_mib = 256;               // tile size of the non-resident pipelines (CODEX_COMMIT_TILE_MIB)
+  int ramp_mode = 1;                   // how a pinned host slot's pipeline starts (CODEX_COMMIT_RAMP; see hash_cells_pinned)
   void* h_pinned[2] = {nullptr, nullptr};   // pinned read buffers of cdx_slot_commit_file
   size_t pinned_bytes = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
@@ -111,6 +112,15 @@ static inline unsigned block_for(const cdx_ctx* ctx, size_t n) {
 
 extern "C" int cdx_abi_version(void) { return CDX_ABI_VERSION; }
 
+extern "C" int cdx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
 extern "C" const char* cdx_status_string(int s) {
   switch (s) {
     case CDX_OK: return "ok";
@@ -139,6 +149,7 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
     const int n = atoi(v);
     if (n >= 2 && n <= CDX_MAX_STAGE) ctx->stage_tiles = n;
   }
+  if (const char* v = getenv("CODEX_COMMIT_RAMP")) ctx->ramp_mode = v[0] != '0';
   if (const char* v = getenv("CODEX_COMMIT_TILE_MIB")) {
     const long n = atol(v);
     if (n >= 16 && n <= 4096) ctx->tile_mib = (size_t)n;
@@ -685,16 +696,25 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));  // and the staging tiles may still be read by earlier work on it
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_join, 0));
   size_t done = 0;
-  const size_t first_tile = tile_blocks / 8 ? tile_blocks / 8 : 1;
+  // Start of the pipeline.  The copy of tile 0 is the only one nothing overlaps, so it is short; after that the copy
+  // of tile t+1 has to hide behind the sponge of tile t, i.e. size(t+1)/copy rate <= size(t)/sponge rate.  With the
+  // ramp mode (CODEX_COMMIT_RAMP, default 1) tiles grow by a quarter per step from 1/4 tile -- the growth a GPU can still
+  // hide when eight of them share the host's PCIe/memory path (23 GB/s against the sponge's 18.4) -- instead of jumping
+  // from 1/8 tile to 7/8 (mode 0, round 1).
   const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
+  size_t cur = ctx->ramp_mode ? (tile_blocks / 4 ? tile_blocks / 4 : 1) : (tile_blocks / 8 ? tile_blocks / 8 : 1);
   for (int t = 0; done < n_blocks; ++t) {
     const int b = t % NS;
     cudaStream_t cs = (t & 1) ? ctx->stream2 : ctx->stream;
     cudaStream_t cp = (t & 1) ? ctx->copy_stream2 : ctx->copy_stream;
-    // the copy of tile 0 is the only one nothing overlaps: keep it short (1/8 tile), then realign with tile 1
     size_t want = tile_blocks;
-    if (ramp && t == 0) want = first_tile;
-    else if (ramp && t == 1) want = tile_blocks - first_tile;
+    if (ramp && ctx->ramp_mode) {
+      want = cur < tile_blocks ? cur : tile_blocks;
+      cur += cur / 4 ? cur / 4 : 1;
+    } else if (ramp) {
+      if (t == 0) want = cur;
+      else if (t == 1) want = tile_blocks - cur;
+    }
     const size_t nb = n_blocks - done < want ? n_blocks - done : want;
     if (t >= NS) CU_TRY(ctx, cudaStreamWaitEvent(cp, ctx->ev_consumed[b], 0));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, cp));

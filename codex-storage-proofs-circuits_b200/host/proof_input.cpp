@@ -152,8 +152,8 @@ Backend::~Backend() {
   cdx_ctx_destroy(ctx_);
 }
 int Backend::visibleGpus() const {
-  int n = 1;
-  for (cdx_ctx* probe = nullptr; n < 64 && cdx_ctx_create(device_ + n, &probe) == CDX_OK; ++n) cdx_ctx_destroy(probe);
+  int n = cdx_device_count() - device_;             // this backend's device and the ones after it
+  if (n < 1) n = 1;
   if (const char* cap = std::getenv("CODEX_COMMIT_GPUS")) {
     const int c = std::atoi(cap);
     if (c >= 1 && c < n) n = c;

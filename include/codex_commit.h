@@ -46,6 +46,8 @@ typedef struct cdx_slot cdx_slot; /* a committed slot: every Merkle layer reside
 
 /* ---- context ------------------------------------------------------------------------------------------ */
 int cdx_abi_version(void);
+/* number of CUDA devices this process can see (0 without a driver or a device); creates no context */
+int cdx_device_count(void);
 int cdx_ctx_create(int device, cdx_ctx** out);
 void cdx_ctx_destroy(cdx_ctx* ctx);
 const char* cdx_last_error(const cdx_ctx* ctx);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Host-buffer (e2e) commit rate per rank for different staging settings, with every rank streaming at once; run under
 torchrun with N ranks (or alone).  Also measures the raw pinned H2D rate per rank under the same contention.
-   CODEX_COMMIT_STAGE_TILES (2..4) x CODEX_COMMIT_TILE_MIB are read when a context is created, so one process can try
+   CODEX_COMMIT_STAGE_TILES (2..4) x CODEX_COMMIT_TILE_MIB x CODEX_COMMIT_RAMP (SWEEP_SETTINGS=3x256x1,3x256x0,...) are read when a context is created, so one process can try
    several.  Prints one JSON line per setting on rank 0: min / mean / max over ranks."""
 import importlib, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -62,8 +62,10 @@ if rank == 0:
 del d
 c0.close()
 settings = [s.split("x") for s in os.environ.get("SWEEP_SETTINGS", "2x256,3x256,4x256,3x128,3x512,2x512").split(",")]
-for tiles, mib in settings:
-    os.environ["CODEX_COMMIT_STAGE_TILES"], os.environ["CODEX_COMMIT_TILE_MIB"] = tiles, mib
+for st in settings:
+    tiles, mib = st[0], st[1]
+    ramp = st[2] if len(st) > 2 else "1"
+    os.environ["CODEX_COMMIT_STAGE_TILES"], os.environ["CODEX_COMMIT_TILE_MIB"], os.environ["CODEX_COMMIT_RAMP"] = tiles, mib, ramp
     ctx = pkg.Context(local)
     with ctx.slot_commit_host(hn) as s:
         assert s.root == root
@@ -78,7 +80,7 @@ for tiles, mib in settings:
     assert r == root
     mn, mean, mx = reduce3(3 * n_bytes / dt / 1e9)
     if rank == 0:
-        print(json.dumps({"what": "e2e commit from pinned host memory", "stage_tiles": int(tiles), "tile_mib": int(mib), "ranks": world,
+        print(json.dumps({"what": "e2e commit from pinned host memory", "stage_tiles": int(tiles), "tile_mib": int(mib), "ramp_mode": int(ramp), "ranks": world,
                           "GB_per_s_min": mn, "mean": mean, "max": mx, "aggregate_at_min": mn * world}), flush=True)
     ctx.close()
 if world > 1:
