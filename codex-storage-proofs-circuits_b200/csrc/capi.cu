@@ -42,7 +42,7 @@ struct cdx_ctx {
   int stage_count = 0;
   int stage_tiles = 3;                 // tiles in flight for pinned host slots (CODEX_COMMIT_STAGE_TILES = 2..4)
   size_t tile_mib = 256;               // tile size of the non-resident pipelines (CODEX_COMMIT_TILE_MIB)
-  int ramp_mode = 1;                   // how a pinned host slot's pipeline starts (CODEX_COMMIT_RAMP; see hash_cells_pinned)
+  int ramp_mode = 0;                   // how a pinned host slot's pipeline starts (CODEX_COMMIT_RAMP; see hash_cells_pinned)
   void* h_pinned[2] = {nullptr, nullptr};   // pinned read buffers of cdx_slot_commit_file
   size_t pinned_bytes = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
@@ -696,11 +696,10 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));  // and the staging tiles may still be read by earlier work on it
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_join, 0));
   size_t done = 0;
-  // Start of the pipeline.  The copy of tile 0 is the only one nothing overlaps, so it is short; after that the copy
-  // of tile t+1 has to hide behind the sponge of tile t, i.e. size(t+1)/copy rate <= size(t)/sponge rate.  With the
-  // ramp mode (CODEX_COMMIT_RAMP, default 1) tiles grow by a quarter per step from 1/4 tile -- the growth a GPU can still
-  // hide when eight of them share the host's PCIe/memory path (23 GB/s against the sponge's 18.4) -- instead of jumping
-  // from 1/8 tile to 7/8 (mode 0, round 1).
+  // Start of the pipeline.  The copy of tile 0 is the only one nothing overlaps, so it is short (1/8 tile), then tile 1
+  // realigns with the tile grid (7/8).  CODEX_COMMIT_RAMP=1 selects a gradual start instead (tiles grow by a quarter per
+  // step from 1/4 tile): measured +0.5 % end to end on one GPU, but -0.7 % with eight GPUs sharing the host's PCIe/memory
+  // path (profiles/r2_e2e_sweep_ramp_n1.txt, r2_e2e_sweep_ramp_n8.txt), so it is not the default.
   const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
   size_t cur = ctx->ramp_mode ? (tile_blocks / 4 ? tile_blocks / 4 : 1) : (tile_blocks / 8 ? tile_blocks / 8 : 1);
   for (int t = 0; done < n_blocks; ++t) {
@@ -873,7 +872,9 @@ static int hash_cells_source(cdx_ctx* ctx, const SlotSource& src, size_t n_bytes
 }
 
 // A slot (whole_slot) or a block range of one, from any non-resident source: cell hashes through the matching pipeline,
-// then block trees and the local slot levels (and the top tree for a whole slot) on ctx->stream.  Returns synchronised.
+// then block trees and the local slot levels (and the top tree for a whole slot) on ctx->stream.  With `sync` it returns
+// synchronised (the public single-slot entry points); without, the work is queued and the source bytes must stay valid
+// until the caller synchronises (the dataset commit queues all of a rank's slots and waits once).
 // n_bytes == 0 is an empty shard (sharded entry points only).
 static int commit_from_source(cdx_ctx* ctx, const SlotSource& src, size_t n_bytes, size_t cell_size, size_t block_size, uint64_t first_block,
                               uint64_t n_total_blocks, int top_level, bool whole_slot, bool sync, cdx_slot** out) {

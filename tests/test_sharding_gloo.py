@@ -200,3 +200,38 @@ def test_dataset_planning_helpers(pkg):
         loads = [sum(blocks[k] for k in b) for b in bins]
         assert max(loads) <= 1.02 * sum(blocks) / world                        # LPT on 256 items: within 2 % of even
     assert dataset.lpt_assign([5], 4) == [[0], [], [], []]
+
+
+def _id_worker(rank, world, port, out_q):
+    """the first half of sharded.comm_from_torch, up to the point where a GPU is needed: the library creates the NCCL id on
+    rank 0 (cdx_comm_unique_id, dlopen of libnccl.so.2 -- no device involved), torch.distributed broadcasts the 128 bytes"""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        capi = importlib.import_module(PKG).capi
+        t = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(t, src=0)
+        out_q.put((rank, bytes(t.numpy())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_communicator_id_bootstrap_over_gloo(pkg):
+    try:
+        pkg.capi.comm_unique_id()
+    except pkg.CodexCommitError:
+        pytest.skip("libnccl.so.2 is not loadable on this machine")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_id_worker, args=(r, world, 29611, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(got[0]) == 128 and got[0] == got[1] and any(got[0])
