@@ -81,6 +81,7 @@ SYMBOLS = {
     "cdx_slot_cell_paths_sharded": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
     "cdx_slot_prove_batch_sharded": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp, _vp]),
     "cdx_dataset_commit": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, C.c_int64, _pp]),
+    "cdx_dataset_plan": (_int, [C.POINTER(_u64), _sz, _sz, _int, C.POINTER(_int)]),
     "cdx_dataset_free": (None, [_vp]),
     "cdx_dataset_root": (_int, [_vp, _vp]),
     "cdx_dataset_slot_roots": (_int, [_vp, _vp]),
@@ -150,6 +151,18 @@ def block_ranges_top_level(n_total_blocks: int, ranges) -> int:
     if rc != CDX_OK:
         raise CodexCommitError(rc, "cdx_block_ranges_top_level: ranges must be contiguous and cover the slot")
     return t.value
+
+
+def dataset_plan(slot_bytes: Sequence[int], n_ranks: int, block_size: int = 65536) -> List[int]:
+    """cdx_dataset_plan -> owner rank per slot, -1 = block-range-sharded over all ranks (no GPU needed)"""
+    lib = load_library()
+    n = len(slot_bytes)
+    sb = (C.c_uint64 * max(n, 1))(*slot_bytes)
+    owner = (C.c_int * max(n, 1))()
+    rc = lib.cdx_dataset_plan(sb, n, block_size, n_ranks, owner)
+    if rc != CDX_OK:
+        raise CodexCommitError(rc, "cdx_dataset_plan")
+    return list(owner)[:n]
 
 
 def comm_unique_id() -> bytes:

@@ -676,6 +676,18 @@ static int commit_desc(cdx_ctx* ctx, cdx_comm* comm, const cdx_slot_desc& d, siz
   return rc;
 }
 
+extern "C" int cdx_dataset_plan(const uint64_t* slot_bytes, size_t n_slots, size_t block_size, int n_ranks, int* owner_out) {
+  if (!slot_bytes || !owner_out || n_slots == 0 || block_size == 0 || n_ranks < 1) return CDX_ERR_ARG;
+  std::vector<uint64_t> blocks(n_slots);
+  for (size_t k = 0; k < n_slots; ++k) {
+    if (slot_bytes[k] == 0 || slot_bytes[k] % block_size) return CDX_ERR_SIZE;
+    blocks[k] = slot_bytes[k] / block_size;
+  }
+  const DatasetPlan plan = plan_dataset(blocks, n_ranks, block_size);
+  for (size_t k = 0; k < n_slots; ++k) owner_out[k] = plan.owner[k];
+  return CDX_OK;
+}
+
 extern "C" void cdx_dataset_free(cdx_dataset* ds) {
   if (!ds) return;
   cdx_slot_free(ds->kept);

@@ -285,6 +285,9 @@ typedef struct cdx_dataset cdx_dataset;
  * reference/haskell/src/Sampling.hs:66-70,84. */
 int cdx_dataset_commit(cdx_ctx* ctx, cdx_comm* comm, const cdx_slot_desc* slots, size_t n_slots, size_t cell_size, size_t block_size,
                        int64_t keep_slot, cdx_dataset** out);
+/* The plan cdx_dataset_commit follows, without committing anything (pure host function, no GPU needed): owner_out[k] = the
+ * rank that commits slot k whole (alone or in a batch), or -1 if slot k is block-range-sharded over all ranks. */
+int cdx_dataset_plan(const uint64_t* slot_bytes, size_t n_slots, size_t block_size, int n_ranks, int* owner_out);
 void cdx_dataset_free(cdx_dataset* ds);
 int cdx_dataset_root(const cdx_dataset* ds, uint8_t root_out[32]);
 /* all slot roots, n_slots * 32 bytes */

@@ -388,7 +388,7 @@ def test_sharded_entry_points_single_rank(ctx, torch_mod):
     comm.destroy()
 
 
-def _nccl_rank(rank, world, id_q, out_q, n_blocks):
+def _nccl_rank(rank, world, id_q, out_q, n_blocks, extra=None):
     """one process per GPU: the library's own communicator (the id travels through a multiprocessing queue -- no
     torch.distributed anywhere), sharded commit, collective paths, dataset commit"""
     import importlib as il
@@ -432,12 +432,21 @@ def _nccl_rank(rank, world, id_q, out_q, n_blocks):
     ds = ctx.dataset_commit(comm, dataset.synthetic_descs([16384 * world, 5], 6), keep_slot=0)   # the kept slot is the sharded one
     res["dataset_sharded_keep"] = (ds.root, ds.slot_roots, ds.stats, ds.prove(7, 6, 32))
     ds.free()
+    # sharded members that are NOT generated: a file (each rank preads its own block range) and host memory (each rank
+    # copies its own range); both are big enough (256 MiB per rank) to be sharded
+    if extra is not None:
+        import numpy as np
+        path, n_bytes = extra
+        host = np.fromfile(path, dtype=np.uint8)
+        ds = ctx.dataset_commit(comm, [(pkg.capi.SRC_FILE, path, n_bytes), (pkg.capi.SRC_HOST, host, n_bytes), (pkg.capi.SRC_SYNTHETIC, 9, 65536)], keep_slot=0)
+        res["dataset_file_host"] = (ds.root, ds.slot_roots, ds.stats, ds.prove(3, 4, 32))
+        ds.free()
     comm.destroy()
     ctx.close()
     out_q.put((rank, res))
 
 
-def test_nccl_sharded_and_dataset_two_gpus(ctx, orc, torch_mod):
+def test_nccl_sharded_and_dataset_two_gpus(ctx, orc, torch_mod, tmp_path):
     """the NCCL path proper (skipped below 2 GPUs): two processes, two GPUs, the library's communicator; the sharded root,
     paths and proofs equal the whole-slot ones computed on one GPU, for a power-of-two slot, a ragged one and a one-block
     slot (rank 1 holds an EMPTY shard); the two-rank dataset equals the one-rank dataset"""
@@ -449,7 +458,11 @@ def test_nccl_sharded_and_dataset_two_gpus(ctx, orc, torch_mod):
     world, n_blocks = 2, [4096, 1000, 1]
     mpc = mp.get_context("spawn")
     id_q, out_q = mpc.Queue(), mpc.Queue()
-    procs = [mpc.Process(target=_nccl_rank, args=(r, world, id_q, out_q, n_blocks)) for r in range(world)]
+    big = 8192 * world * 65536                                              # 1 GiB: 512 MiB per rank, a power-of-two cell count
+    big_path = str(tmp_path / "big_slot.dat")
+    big_dev = synthetic(ctx, torch, big, seed=21)
+    big_dev.cpu().numpy().tofile(big_path)
+    procs = [mpc.Process(target=_nccl_rank, args=(r, world, id_q, out_q, n_blocks, (big_path, big))) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(out_q.get(timeout=600) for _ in range(world))
@@ -479,3 +492,11 @@ def test_nccl_sharded_and_dataset_two_gpus(ctx, orc, torch_mod):
     for r in range(world):
         root, roots, stats, proof = results[r]["dataset_sharded_keep"]
         assert (root, roots, proof) == one, r
+    # file- and host-backed sharded members against the same bytes committed resident on one GPU
+    with ctx.slot_commit_dev(big_dev.data_ptr(), big) as whole:
+        (idx,), (paths,), (leaves,) = whole.prove_batch([3], 4, 32)
+        for r in range(world):
+            root, roots, stats, proof = results[r]["dataset_file_host"]
+            assert roots[0] == roots[1] == whole.root, r
+            assert stats["sharded"] == 2 and stats["bytes_local"] in (big, big + 65536)
+            assert proof == (idx, paths, leaves), r

@@ -200,6 +200,21 @@ def test_dataset_planning_helpers(pkg):
         loads = [sum(blocks[k] for k in b) for b in bins]
         assert max(loads) <= 1.02 * sum(blocks) / world                        # LPT on 256 items: within 2 % of even
     assert dataset.lpt_assign([5], 4) == [[0], [], [], []]
+    # the plan the library follows (cdx_dataset_plan): without sharded members it is the LPT packing above
+    for world in (1, 2, 4, 8):
+        owner = pkg.capi.dataset_plan([b * 65536 for b in blocks], world)
+        assert all(o >= 0 for o in owner)                                       # 256 slots of <= 100 GiB: nothing exceeds a quarter of a share
+        bins = dataset.lpt_assign(blocks, world)
+        assert owner == [next(r for r in range(world) if k in bins[r]) for k in range(256)]
+    # sharding rule: more than a quarter of the ideal share AND at least 256 MiB per rank
+    gib = (1 << 30) // 65536
+    assert pkg.capi.dataset_plan([100 * gib * 65536] * 4, 8) == [-1, -1, -1, -1]            # four 100 GiB slots on 8 GPUs: all sharded
+    assert pkg.capi.dataset_plan([64 * 65536] * 11, 8) == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2]  # config 1: 4 MiB slots are never sharded
+    plan = pkg.capi.dataset_plan([100 * gib * 65536] + [gib * 65536] * 20, 8)                # one dominant slot among small ones
+    assert plan[0] == -1 and sorted(set(plan[1:])) == list(range(8))
+    assert pkg.capi.dataset_plan([100 * gib * 65536], 1) == [0]                              # one rank: nothing to shard over
+    with pytest.raises(pkg.CodexCommitError):
+        pkg.capi.dataset_plan([65536 + 1], 2)
 
 
 def _id_worker(rank, world, port, out_q):
