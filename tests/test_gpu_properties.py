@@ -500,3 +500,52 @@ def test_nccl_sharded_and_dataset_two_gpus(ctx, orc, torch_mod, tmp_path):
             assert roots[0] == roots[1] == whole.root, r
             assert stats["sharded"] == 2 and stats["bytes_local"] in (big, big + 65536)
             assert proof == (idx, paths, leaves), r
+
+
+def test_fuzz_geometries_batch_dataset_and_single_agree_with_oracle(ctx, orc, torch_mod):
+    """seeded fuzz over cell size (multiples of 4: both the TMA and the plain-load kernels), cells per block (powers of two
+    incl. one-cell blocks), ragged slot sizes and batch composition: the batched entry point, the dataset commit and the
+    single-slot commit must agree, and the oracle must agree with them on a slot of every case"""
+    import bench
+    capi = importlib.import_module(PKG).capi
+    torch = torch_mod
+    rnd = random.Random(20261018)
+    for case in range(24):
+        cell = rnd.choice([64, 96, 128, 160, 256, 388, 512, 1024, 2048, 2052, 4096])
+        cpb = rnd.choice([1, 2, 4, 8, 32, 64])
+        block = cell * cpb
+        n_slots = rnd.randint(1, 9)
+        blocks = [rnd.choice([1, 1, 2, 3, 5, 8, 13, 33, 64, 100]) for _ in range(n_slots)]
+        sizes = [b * block for b in blocks]
+        total = sum(sizes)
+        if total % 8:                                         # the synthetic generator writes 8-byte words
+            continue
+        d = synthetic(ctx, torch, total, seed=1000 + case)
+        roots = ctx.slots_commit_batch_dev(d.data_ptr(), sizes, cell, block)
+        host = d.cpu().numpy()
+        off, singles = 0, []
+        for sz in sizes:
+            if (d.data_ptr() + off) % 16 == 0:
+                with ctx.slot_commit_dev(d.data_ptr() + off, sz, cell, block) as s:
+                    singles.append(s.root)
+            else:                                            # the device entry point wants a 16-byte aligned base
+                with ctx.slot_commit_host(host[off:off + sz].copy(), cell, block) as s:
+                    singles.append(s.root)
+            off += sz
+        assert roots == singles, (case, cell, cpb, blocks)
+        k = rnd.randrange(n_slots)
+        o = sum(sizes[:k])
+        part = host[o:o + sizes[k]].copy()
+        assert roots[k] == orc.commit_slot((part.ctypes.data, sizes[k]), cell, block, n_threads=4)[0], (case, cell, cpb, blocks, k)
+        descs, o = [], 0
+        for sz in sizes:
+            descs.append((capi.SRC_HOST, host[o:o + sz].copy(), sz))
+            o += sz
+        keep = rnd.randrange(n_slots)
+        with ctx.dataset_commit(None, descs, cell, block, keep_slot=keep) as ds:
+            assert ds.slot_roots == roots, (case, cell, cpb, blocks)
+            assert ds.root == orc.merkle_root(roots)
+            n_cells = blocks[keep] * cpb
+            if n_cells & (n_cells - 1) == 0 and n_cells > 1:
+                idx, paths, leaves = ds.prove(case + 1, 3, 40)
+                assert idx == [orc.cell_index(case + 1, roots[keep], n_cells, c) for c in range(1, 4)]
