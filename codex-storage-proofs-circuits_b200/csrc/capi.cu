@@ -42,7 +42,10 @@ struct cdx_ctx {
   int stage_count = 0;
   int stage_tiles = 3;                 // tiles in flight for pinned host slots (CODEX_COMMIT_STAGE_TILES = 2..4)
   size_t tile_mib = 256;               // tile size of the non-resident pipelines (CODEX_COMMIT_TILE_MIB)
-  int ramp_mode = 0;                   // how a pinned host slot's pipeline starts (CODEX_COMMIT_RAMP; see hash_cells_pinned)
+  int ramp_mode = 0;                   // how a pinned host slot's pipeline starts (CODEX_COMMIT_RAMP = 0, 1 or 2 = auto; see hash_cells_pinned)
+  cudaEvent_t ev_rate[2] = {nullptr, nullptr};   // around one full-size tile copy of the last pinned commit: the H2D rate this GPU really gets
+  size_t rate_bytes = 0;
+  double h2d_gbs = 0.0;                // last measured rate (0 = not measured yet)
   void* h_pinned[2] = {nullptr, nullptr};   // pinned read buffers of cdx_slot_commit_file
   size_t pinned_bytes = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
@@ -149,7 +152,7 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
     const int n = atoi(v);
     if (n >= 2 && n <= CDX_MAX_STAGE) ctx->stage_tiles = n;
   }
-  if (const char* v = getenv("CODEX_COMMIT_RAMP")) ctx->ramp_mode = v[0] != '0';
+  if (const char* v = getenv("CODEX_COMMIT_RAMP")) ctx->ramp_mode = v[0] == '0' ? 0 : (v[0] == '1' ? 1 : 2);
   if (const char* v = getenv("CODEX_COMMIT_TILE_MIB")) {
     const long n = atol(v);
     if (n >= 16 && n <= 4096) ctx->tile_mib = (size_t)n;
@@ -174,6 +177,7 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
   }
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev_rate[i]);
   if (e != cudaSuccess) {
     delete ctx;
     return CDX_ERR_CUDA;
@@ -193,6 +197,7 @@ extern "C" void cdx_ctx_destroy(cdx_ctx* ctx) {
   for (int i = 0; i < 2; ++i) {
     if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
     if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    if (ctx->ev_rate[i]) cudaEventDestroy(ctx->ev_rate[i]);
   }
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -696,18 +701,34 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_join, 0));  // and the staging tiles may still be read by earlier work on it
   CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_join, 0));
   size_t done = 0;
-  // Start of the pipeline.  The copy of tile 0 is the only one nothing overlaps, so it is short (1/8 tile), then tile 1
-  // realigns with the tile grid (7/8).  CODEX_COMMIT_RAMP=1 selects a gradual start instead (tiles grow by a quarter per
-  // step from 1/4 tile): measured +0.5 % end to end on one GPU, but -0.7 % with eight GPUs sharing the host's PCIe/memory
-  // path (profiles/r2_e2e_sweep_ramp_n1.txt, r2_e2e_sweep_ramp_n8.txt), so it is not the default.
+  // Start of the pipeline.  The copy of tile 0 is the only one nothing overlaps, so it is short; after that the copy of
+  // tile t+1 has to hide behind the sponge of tile t.  Two starts:
+  //   mode 0  1/8 tile, then 7/8 (realigns with the tile grid);
+  //   mode 1  gradual: tiles grow by a quarter per step from 1/4 tile.
+  // Measured (profiles/r2_e2e_sweep_ramp_n1.txt, r2_e2e_sweep_ramp_n8.txt): the gradual start gains 0.5 % end to end when this
+  // GPU has the host's PCIe/memory path to itself (H2D 55 GB/s) and LOSES 0.7 % when eight GPUs share it (23-35 GB/s per
+  // GPU).  So the default (mode 2) decides per call from the H2D rate this context measured on its previous pinned
+  // commit (two events around one full-size tile copy, read back here without waiting): gradual above 40 GB/s, else
+  // mode 0; the first commit of a context uses mode 0.  CODEX_COMMIT_RAMP=0/1 pins the choice.
   const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
-  size_t cur = ctx->ramp_mode ? (tile_blocks / 4 ? tile_blocks / 4 : 1) : (tile_blocks / 8 ? tile_blocks / 8 : 1);
+  if (ctx->rate_bytes) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_rate[0], ctx->ev_rate[1]) == cudaSuccess && ms > 0.f) {
+      ctx->h2d_gbs = (double)ctx->rate_bytes / (ms * 1e6);
+      ctx->rate_bytes = 0;
+    } else {
+      cudaGetLastError();                                               // not finished yet (cannot happen after a synchronised commit)
+    }
+  }
+  const bool gradual = ctx->ramp_mode == 1 || (ctx->ramp_mode == 2 && ctx->h2d_gbs > 40.0);
+  size_t cur = gradual ? (tile_blocks / 4 ? tile_blocks / 4 : 1) : (tile_blocks / 8 ? tile_blocks / 8 : 1);
+  bool rate_armed = false;
   for (int t = 0; done < n_blocks; ++t) {
     const int b = t % NS;
     cudaStream_t cs = (t & 1) ? ctx->stream2 : ctx->stream;
     cudaStream_t cp = (t & 1) ? ctx->copy_stream2 : ctx->copy_stream;
     size_t want = tile_blocks;
-    if (ramp && ctx->ramp_mode) {
+    if (ramp && gradual) {
       want = cur < tile_blocks ? cur : tile_blocks;
       cur += cur / 4 ? cur / 4 : 1;
     } else if (ramp) {
@@ -716,7 +737,14 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
     }
     const size_t nb = n_blocks - done < want ? n_blocks - done : want;
     if (t >= NS) CU_TRY(ctx, cudaStreamWaitEvent(cp, ctx->ev_consumed[b], 0));
+    const bool measure = !rate_armed && nb == tile_blocks && t >= NS;    // a full tile in steady state (its buffer wait is already behind it)
+    if (measure) CU_TRY(ctx, cudaEventRecord(ctx->ev_rate[0], cp));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], data + done * block_size, nb * block_size, cudaMemcpyHostToDevice, cp));
+    if (measure) {
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_rate[1], cp));
+      ctx->rate_bytes = nb * block_size;
+      rate_armed = true;
+    }
     CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], cp));
     CU_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_copied[b], 0));
     int hr = launch_hash_cells(ctx, ctx->d_stage[b], nb * cpb, cell_size, d_hashes + 32 * done * cpb, cs);
