@@ -42,7 +42,7 @@ struct cdx_ctx {
   int stage_count = 0;
   int stage_tiles = 3;                 // tiles in flight for pinned host slots (CODEX_COMMIT_STAGE_TILES = 2..4)
   size_t tile_mib = 256;               // tile size of the non-resident pipelines (CODEX_COMMIT_TILE_MIB)
-  int ramp_mode = 0;                   // how a pinned host slot's pipeline starts (CODEX_COMMIT_RAMP = 0, 1 or 2 = auto; see hash_cells_pinned)
+  int ramp_mode = 2;                   // how a pinned host slot's pipeline starts (CODEX_COMMIT_RAMP = 0, 1 or 2 = auto; see hash_cells_pinned)
   cudaEvent_t ev_rate[2] = {nullptr, nullptr};   // around one full-size tile copy of the last pinned commit: the H2D rate this GPU really gets
   size_t rate_bytes = 0;
   double h2d_gbs = 0.0;                // last measured rate (0 = not measured yet)
