@@ -708,7 +708,7 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
   // Measured (profiles/r2_e2e_sweep_ramp_n1.txt, r2_e2e_sweep_ramp_n8.txt): the gradual start gains 0.5 % end to end when this
   // GPU has the host's PCIe/memory path to itself (H2D 55 GB/s) and LOSES 0.7 % when eight GPUs share it (23-35 GB/s per
   // GPU).  So the default (mode 2) decides per call from the H2D rate this context measured on its previous pinned
-  // commit (two events around one full-size tile copy, read back here without waiting): gradual above 40 GB/s, else
+  // commit (two events around one full-size tile copy, read back here without waiting): gradual above 48 GB/s, else
   // mode 0; the first commit of a context uses mode 0.  CODEX_COMMIT_RAMP=0/1 pins the choice.
   const bool ramp = n_blocks > tile_blocks && tile_blocks >= 8;
   if (ctx->rate_bytes) {
@@ -720,7 +720,7 @@ static int hash_cells_pinned(cdx_ctx* ctx, const uint8_t* data, size_t n_bytes, 
       cudaGetLastError();                                               // not finished yet (cannot happen after a synchronised commit)
     }
   }
-  const bool gradual = ctx->ramp_mode == 1 || (ctx->ramp_mode == 2 && ctx->h2d_gbs > 40.0);
+  const bool gradual = ctx->ramp_mode == 1 || (ctx->ramp_mode == 2 && ctx->h2d_gbs > 48.0);
   size_t cur = gradual ? (tile_blocks / 4 ? tile_blocks / 4 : 1) : (tile_blocks / 8 ? tile_blocks / 8 : 1);
   bool rate_armed = false;
   for (int t = 0; done < n_blocks; ++t) {
