@@ -52,6 +52,7 @@ struct cdx_ctx {
   uint64_t launches = 0;
   bool no_bounce = false;              // CODEX_COMMIT_NO_BOUNCE=1: pageable host slots straight through cudaMemcpyAsync (A/B only)
   bool tma_smem_set = false;
+  size_t max_launch_cells = (size_t)1 << 30;   // cells per cell-sponge launch (CODEX_COMMIT_MAX_LAUNCH_CELLS lowers it so tests can cross the boundary)
   bool plain_loads = false;            // CODEX_COMMIT_PLAIN_LOADS=1: per-thread global loads instead of the TMA-staged rows (A/B only)
   char err[256] = {0};
 };
@@ -148,6 +149,10 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   ctx->device = device;
   if (const char* v = getenv("CODEX_COMMIT_PLAIN_LOADS")) ctx->plain_loads = v[0] == '1';
   if (const char* v = getenv("CODEX_COMMIT_NO_BOUNCE")) ctx->no_bounce = v[0] == '1';
+  if (const char* v = getenv("CODEX_COMMIT_MAX_LAUNCH_CELLS")) {
+    const long long n = atoll(v);
+    if (n >= 32 && n <= (1ll << 30)) ctx->max_launch_cells = (size_t)n & ~(size_t)31;   // whole warps
+  }
   if (const char* v = getenv("CODEX_COMMIT_STAGE_TILES")) {
     const int n = atoi(v);
     if (n >= 2 && n <= CDX_MAX_STAGE) ctx->stage_tiles = n;
@@ -254,7 +259,7 @@ static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, s
   if (encode && cell_size % CDX_SEG_BYTES == 0 && cell_size >= 64 && cell_size < (1u << 31) && (uintptr_t)d_data % 16 == 0) {
     // tensor coordinates are signed 32-bit (a row index >= 2^31 would read as out of bounds, i.e. as zeros): launches of at
     // most 2^30 cells, each with its own tensor-map base
-    const size_t max_cells = (size_t)1 << 30;
+    const size_t max_cells = ctx->max_launch_cells;
     const unsigned blk = block_for(ctx, n_cells);
     const size_t smem_max = 128 + (CDX_BLOCK / 32) * (CDX_RING_SLOTS * CDX_BOX_BYTES + 8 * CDX_RING_SLOTS);
     const size_t smem = 128 + (blk / 32) * (CDX_RING_SLOTS * CDX_BOX_BYTES + 8 * CDX_RING_SLOTS);
@@ -278,7 +283,7 @@ static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, s
     }
     return CDX_OK;
   }
-  const size_t max_cells = (size_t)1 << 30;                                  // keeps the grid below 2^31 CTAs
+  const size_t max_cells = ctx->max_launch_cells;                            // keeps the grid below 2^31 CTAs
   for (size_t c0 = 0; c0 < n_cells; c0 += max_cells) {
     const size_t nc = n_cells - c0 < max_cells ? n_cells - c0 : max_cells;
     const unsigned blk = block_for(ctx, nc);

@@ -549,3 +549,28 @@ def test_fuzz_geometries_batch_dataset_and_single_agree_with_oracle(ctx, orc, to
             if n_cells & (n_cells - 1) == 0 and n_cells > 1:
                 idx, paths, leaves = ds.prove(case + 1, 3, 40)
                 assert idx == [orc.cell_index(case + 1, roots[keep], n_cells, c) for c in range(1, 4)]
+
+
+def test_cell_sponge_launch_boundary(pkg, ctx, torch_mod):
+    """slots of more than 2^30 cells are hashed by several launches, each with its own tensor-map base (TMA row
+    coordinates are signed 32-bit).  CODEX_COMMIT_MAX_LAUNCH_CELLS lowers that boundary for a fresh context so that a small
+    slot crosses it several times, on the TMA path (64-byte cells) and on the plain-load path (100-byte cells): same roots,
+    same cell hashes as the single-launch context"""
+    import os
+    torch = torch_mod
+    cases = [(64, 64 * 32, 1000 * 32), (100, 100 * 8, 777 * 8), (2048, 65536, 300 * 32)]
+    os.environ["CODEX_COMMIT_MAX_LAUNCH_CELLS"] = "4096"
+    try:
+        small = pkg.Context(0)
+    finally:
+        del os.environ["CODEX_COMMIT_MAX_LAUNCH_CELLS"]
+    for cell, block, n_cells in cases:
+        n_bytes = n_cells * cell
+        d = synthetic(ctx, torch, (n_bytes + 7) // 8 * 8, seed=cell)
+        with ctx.slot_commit_dev(d.data_ptr(), n_bytes, cell, block) as a, small.slot_commit_dev(d.data_ptr(), n_bytes, cell, block) as b:
+            assert a.root == b.root, (cell, block)
+            assert a.read_layer(0, 0, 0, n_cells) == b.read_layer(0, 0, 0, n_cells)
+        host = d[:n_bytes].cpu().numpy()
+        with small.slot_commit_host(host, cell, block) as c, ctx.slot_commit_host(host, cell, block) as e:
+            assert c.root == e.root
+    small.close()
