@@ -133,7 +133,8 @@ int cdx_slot_commit_fake(cdx_ctx* ctx, uint64_t seed, size_t n_cells, size_t cel
 /* Sharded commitment (one process per GPU).  This rank holds blocks [first_block, first_block + n_local_blocks)
  * of a slot of n_total_blocks; first_block must be a multiple of 2^top_level, and so must n_local_blocks unless
  * the range ends at n_total_blocks.  Levels 0..top_level of the slot tree are built for the local range; the
- * level-top_level nodes are the sub-tree roots to exchange (all-gather).  cdx_slot_set_top then installs the
+ * level-top_level nodes are the sub-tree roots to exchange (cdx_slot_exchange_top does it over NCCL; these calls are the
+ * pieces it is made of, for hosts that bring their own transport).  cdx_slot_set_top then installs the
  * gathered level and builds the replicated upper levels.  (The reference is single-process; the tree
  * conventions are nim/merkle/bn254.nim:29-60 with the odd-node rule applied to the GLOBAL layer width.) */
 int cdx_slot_commit_range_dev(cdx_ctx* ctx, const void* d_data, size_t n_local_bytes, size_t cell_size, size_t block_size,
@@ -141,7 +142,7 @@ int cdx_slot_commit_range_dev(cdx_ctx* ctx, const void* d_data, size_t n_local_b
 int cdx_slot_commit_range_host(cdx_ctx* ctx, const uint8_t* data, size_t n_local_bytes, size_t cell_size, size_t block_size,
                                uint64_t first_block, uint64_t n_total_blocks, int top_level, cdx_slot** out);
 int cdx_slot_subtree_root_count(const cdx_slot* slot, uint64_t* first_node, uint64_t* n_nodes);
-/* copy this rank's level-top_level nodes into a caller buffer (e.g. a torch tensor handed to NCCL all-gather) */
+/* copy this rank's level-top_level nodes into a caller buffer (a host-provided transport's send buffer) */
 int cdx_slot_subtree_roots_copy_dev(const cdx_slot* slot, void* d_dst, void* stream);
 /* device pointer to this rank's level-top_level nodes (n_nodes * 32 bytes), for NCCL */
 const void* cdx_slot_subtree_roots_dev(const cdx_slot* slot);
