@@ -961,14 +961,19 @@ extern "C" int cdx_group_create(const int* devices, int n_devices, cdx_group** o
   }
   cdx_group* g = new (std::nothrow) cdx_group();
   if (!g) return CDX_ERR_ALLOC;
-  for (int d : devs) {
-    cdx_ctx* c = nullptr;
-    const int rc = cdx_ctx_create(d, &c);
-    if (rc) {
-      cdx_group_destroy(g);
-      return rc;
-    }
-    g->ctx.push_back(c);
+  // one CUDA primary context per device: created in parallel, it is most of the group's start-up time
+  g->ctx.assign(devs.size(), nullptr);
+  {
+    std::vector<int> rcs(devs.size(), CDX_OK);
+    std::vector<std::thread> thr;
+    for (size_t r = 0; r < devs.size(); ++r) thr.emplace_back([&, r]() { rcs[r] = cdx_ctx_create(devs[r], &g->ctx[r]); });
+    for (auto& t : thr) t.join();
+    for (size_t r = 0; r < devs.size(); ++r)
+      if (rcs[r] != CDX_OK) {
+        const int rc = rcs[r];
+        cdx_group_destroy(g);
+        return rc;
+      }
   }
   const int n = (int)devs.size();
   g->comm.assign(n, nullptr);

@@ -407,8 +407,13 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
     }
   }
   DatasetHandles h(be);
+  // All GPUs when it pays: creating the group costs one NCCL initialisation (a second or two for eight GPUs, once per
+  // process), which a single B200 spends committing ~30 GB; a one-shot cli therefore takes the group from 32 GiB up
+  // (CODEX_COMMIT_GROUP_MIN_GIB overrides the threshold; a long-lived host that keeps its Backend pays the start-up once).
   const uint64_t totalBytes = (uint64_t)nslots * descs[0].n_bytes;
-  const bool useGroup = totalBytes >= ((uint64_t)1 << 30) && be.visibleGpus() > 1;
+  double minGib = 32.0;
+  if (const char* v = std::getenv("CODEX_COMMIT_GROUP_MIN_GIB")) minGib = std::atof(v);
+  const bool useGroup = (double)totalBytes >= minGib * (double)((uint64_t)1 << 30) && be.visibleGpus() > 1;
   if (useGroup) {
     h.group = be.group();
     h.ds.assign((size_t)cdx_group_size(h.group), nullptr);

@@ -87,8 +87,9 @@ class Backend {
   cdx_ctx* ctx() const { return ctx_; }
   void check(int rc, const char* what) const;              // throws AssertionDefect on rc != 0
   // Every visible GPU of this process as one group (cdx_group: a context, a communicator rank and a worker thread per
-  // device), created on first use.  generateProofInputBN254 commits datasets of 1 GiB and more through it; the
-  // environment variable CODEX_COMMIT_GPUS caps the number of GPUs (1 = never use the group).
+  // device), created on first use.  generateProofInputBN254 commits datasets of 32 GiB and more through it
+  // (CODEX_COMMIT_GROUP_MIN_GIB changes that threshold); the environment variable CODEX_COMMIT_GPUS caps the number of
+  // GPUs (1 = never use the group).
   cdx_group* group();
   int visibleGpus() const;
  private:

@@ -209,7 +209,9 @@ int main() {
       d.nCells = 32768;
       d.nSlots = 20;
       d.nSamples = 7;
+      setenv("CODEX_COMMIT_GROUP_MIN_GIB", "1", 1);          // the all-GPU path normally starts at 32 GiB
       const SlotProofInput all = generateProofInputBN254(be, h, g, d, 13, felt(424242));
+      unsetenv("CODEX_COMMIT_GROUP_MIN_GIB");
       setenv("CODEX_COMMIT_GPUS", "1", 1);
       const SlotProofInput one = generateProofInputBN254(be, h, g, d, 13, felt(424242));
       unsetenv("CODEX_COMMIT_GPUS");
