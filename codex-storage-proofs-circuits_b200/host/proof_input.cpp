@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -365,6 +366,15 @@ Block dataSetLoadBlockData(Backend& be, const GlobalConfig& g, const DataSetConf
 // ---- nim/gen_input/bn254.nim --------------------------------------------------------------------------------
 
 namespace {
+// CODEX_HOST_TRACE=1: wall-clock milestones of generateProofInputBN254 on stderr
+struct Trace {
+  const bool on = std::getenv("CODEX_HOST_TRACE") != nullptr;
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) const {
+    if (on) std::fprintf(stderr, "[trace] %8.3f s  %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), what);
+  }
+};
+
 // the dataset committed on one GPU (comm == NULL) or on every GPU of the backend's group: handles per rank
 struct DatasetHandles {
   Backend& be;
@@ -407,6 +417,7 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
     }
   }
   DatasetHandles h(be);
+  const Trace trace;
   // All GPUs when it pays: creating the group costs one NCCL initialisation (a second or two for eight GPUs, once per
   // process), which a single B200 spends committing ~30 GB; a one-shot cli therefore takes the group from 32 GiB up
   // (CODEX_COMMIT_GROUP_MIN_GIB overrides the threshold; a long-lived host that keeps its Backend pays the start-up once).
@@ -416,6 +427,7 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
   const bool useGroup = (double)totalBytes >= minGib * (double)((uint64_t)1 << 30) && be.visibleGpus() > 1;
   if (useGroup) {
     h.group = be.group();
+    trace.mark("group of all GPUs created");
     h.ds.assign((size_t)cdx_group_size(h.group), nullptr);
     const int rc = cdx_group_dataset_commit(h.group, descs.data(), descs.size(), (size_t)globCfg.cellSize, (size_t)globCfg.blockSize, slotIdx, h.ds.data());
     if (rc != CDX_OK) throw AssertionDefect(std::string("buildSlotTree (all GPUs): ") + cdx_group_last_error(h.group) + " [" + cdx_status_string(rc) + "]");
@@ -424,6 +436,7 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
     be.check(cdx_dataset_commit(be.ctx(), nullptr, descs.data(), descs.size(), (size_t)globCfg.cellSize, (size_t)globCfg.blockSize, slotIdx, &h.ds[0]),
              "buildSlotTree");
   }
+  trace.mark(useGroup ? "dataset committed on all GPUs" : "dataset committed on one GPU");
   cdx_dataset* ds0 = h.ds[0];
   std::vector<Root> slotRoots((size_t)nslots);
   be.check(cdx_dataset_slot_roots(ds0, slotRoots[0].data()), "treeRoot");
@@ -460,6 +473,7 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
     }
   }
   const std::vector<int64_t> indices(idx64.begin(), idx64.end());
+  trace.mark("indices, cell hashes and paths of all samples");
 
   // mergeMerkleProofs (merkle.nim:86-100) re-hashes every bottom proof and asserts it lands on the top proof's leaf (the
   // block hash held in the slot tree); here that check runs for all samples in ONE batched verifier launch
@@ -492,6 +506,7 @@ SlotProofInput generateProofInputBN254(Backend& be, const HashConfig& hashCfg, c
     cpi.merkleProof = padMerkleProof(merged, globCfg.maxDepth);                         // :63
     out.proofInputs.push_back(std::move(cpi));
   }
+  trace.mark("sampled cells loaded, bottom proofs checked");
   out.dataSetRoot = dsetRoot;
   out.entropy = entropy;
   out.nCells = ncells;
