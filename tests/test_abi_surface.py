@@ -118,3 +118,24 @@ def test_nim_patch_series_applies_to_the_reference(tmp_path):
         assert res.returncode == 0, f + "\n" + res.stdout + res.stderr
     src = (dst / "src" / "gen_input" / "bn254.nim").read_text()
     assert "cdx_group_dataset_commit" in src and "proc generateProofInputBN254*( hashCfg: HashConfig, globCfg: GlobalConfig, dsetCfg: DataSetConfig, slotIdx: SlotIdx, entropy: Entropy ): SlotProofInput[Hash]" in src
+
+
+def build_c_example(tmp_path):
+    import subprocess
+    pkg_dir = os.path.join(ROOT, "codex-storage-proofs-circuits_b200")
+    exe = str(tmp_path / "commit_dataset")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "commit_dataset.c"), "-L" + pkg_dir, "-lcodexcommit", "-Wl,-rpath," + pkg_dir, "-o", exe], check=True)
+    return exe
+
+
+def test_plain_c_example_links_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """examples/commit_dataset.c: the ABI is usable from a C99 compiler (no C++ in the header, every symbol links); without
+    a device the program reports that there is no CPU path"""
+    import subprocess
+    import torch
+    exe = build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the GPU suite runs the example")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 2 and "no CPU path" in res.stderr
