@@ -129,12 +129,12 @@ def _worker(rank, world, port, n_total_blocks, seed, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total_blocks", [13, 16, 21, 1])
-def test_two_rank_sharded_commit_matches_single_process(orc, n_total_blocks):
-    seed, world = 777, 2
+@pytest.mark.parametrize("n_total_blocks,world", [(13, 2), (16, 2), (21, 2), (1, 2), (21, 3), (2, 3)])
+def test_two_rank_sharded_commit_matches_single_process(orc, n_total_blocks, world):
+    seed = 777
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + n_total_blocks
+    port = 29500 + n_total_blocks + 40 * world
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_total_blocks, seed, q)) for r in range(world)]
     for p in procs:
         p.start()
