@@ -49,6 +49,9 @@ struct cdx_ctx {
   void* h_pinned[2] = {nullptr, nullptr};   // pinned read buffers of cdx_slot_commit_file
   size_t pinned_bytes = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+  void* h_scratch = nullptr;           // small pinned buffer for per-call tables uploaded without stalling a busy stream (batch offsets)
+  size_t scratch_bytes = 0;
+  cudaEvent_t ev_scratch = nullptr;    // recorded after the last upload from h_scratch
   uint64_t launches = 0;
   bool no_bounce = false;              // CODEX_COMMIT_NO_BOUNCE=1: pageable host slots straight through cudaMemcpyAsync (A/B only)
   bool tma_smem_set = false;
@@ -177,6 +180,7 @@ extern "C" int cdx_ctx_create(int device, cdx_ctx** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming);
   for (int i = 0; i < CDX_MAX_STAGE && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
@@ -209,6 +213,8 @@ extern "C" void cdx_ctx_destroy(cdx_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
+  if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   delete ctx;
 }
 
@@ -252,6 +258,30 @@ static encode_tiled_fn get_encode_tiled() {
       fn = (encode_tiled_fn)p;
   }
   return fn;
+}
+
+// Make a small host table available to kernels on `st` without stalling it: an asynchronous copy from pageable memory
+// would first wait for everything queued on the stream, and a copy queued ON the stream would sit behind the sponge that
+// runs there.  The device buffer is allocated and filled on the (idle) copy stream from the context's pinned scratch
+// buffer, `st` waits for the event, and the buffer is handed over to `st` for its stream-ordered free.  The scratch
+// buffer is reused only after the previous upload from it has completed.
+static int upload_table(cdx_ctx* ctx, DevBuf& dst, const void* src, size_t bytes, cudaStream_t st) {
+  CU_TRY(ctx, cudaEventSynchronize(ctx->ev_scratch));              // never recorded = complete
+  if (ctx->scratch_bytes < bytes) {
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    ctx->h_scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    const size_t want = bytes < ((size_t)64 << 10) ? ((size_t)64 << 10) : bytes;
+    if (cudaHostAlloc(&ctx->h_scratch, want, cudaHostAllocDefault) != cudaSuccess) return fail(ctx, CDX_ERR_ALLOC, "cudaHostAlloc of %zu bytes failed", want);
+    ctx->scratch_bytes = want;
+  }
+  memcpy(ctx->h_scratch, src, bytes);
+  CU_TRY(ctx, dst.alloc(bytes, ctx->copy_stream));
+  CU_TRY(ctx, cudaMemcpyAsync(dst.p, ctx->h_scratch, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_scratch, ctx->copy_stream));
+  CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
+  dst.st = st;                                                      // freed after the kernels on st that read it
+  return CDX_OK;
 }
 
 static int launch_hash_cells(cdx_ctx* ctx, const void* d_data, size_t n_cells, size_t cell_size, uint8_t* d_out, cudaStream_t st) {

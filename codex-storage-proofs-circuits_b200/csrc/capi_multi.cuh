@@ -76,10 +76,11 @@ static int batch_trees(cdx_ctx* ctx, uint8_t* d_forest, size_t n_cells, size_t c
   for (size_t l = 1; l < n_levels; ++l) upper_nodes += off[l][n_slots];
   std::vector<uint64_t> flat;
   for (size_t l = 0; l < n_levels; ++l) flat.insert(flat.end(), off[l].begin(), off[l].end());
-  CU_TRY(ctx, d_off.alloc(8 * flat.size(), st));
   CU_TRY(ctx, d_upper.alloc(32 * upper_nodes, st));
-  CU_TRY(ctx, cudaMemcpyAsync(d_off.p, flat.data(), 8 * flat.size(), cudaMemcpyHostToDevice, st));
-  CU_TRY(ctx, cudaStreamSynchronize(st));            // `flat` is pageable and dies with this scope
+  {
+    const int rc = upload_table(ctx, d_off, flat.data(), 8 * flat.size(), st);   // no stall of st: the sponge queued on it keeps running
+    if (rc) return rc;
+  }
   const uint64_t* offs = (const uint64_t*)d_off.p;
   const uint8_t* in = cur;                           // level 0 = the block hashes, last layer of the forest
   uint8_t* out = d_upper.u8();
@@ -769,8 +770,15 @@ extern "C" int cdx_dataset_commit(cdx_ctx* ctx, cdx_comm* comm, const cdx_slot_d
       if (rc) return rc;
       rc = batch_finish(ctx, d_forest, n_cells, cpb, bb, st, nullptr, d_batch_roots.u8());
       if (rc) return rc;
-      for (size_t i = 0; i < batch.size(); ++i)
-        CU_TRY(ctx, cudaMemcpyAsync(d_roots.u8() + 32 * batch[i], d_batch_roots.u8() + 32 * i, 32, cudaMemcpyDeviceToDevice, st));
+      {                                                                        // batch roots into their places: one launch, not one copy per slot
+        std::vector<uint64_t> where(batch.begin(), batch.end());
+        DevBuf d_where;
+        rc = upload_table(ctx, d_where, where.data(), 8 * where.size(), st);
+        if (rc) return rc;
+        k_scatter_felts<<<grid_for(2 * where.size(), 256), 256, 0, st>>>(d_batch_roots.u8(), (const uint64_t*)d_where.p, where.size(), d_roots.u8());
+        ctx->launches++;
+        CU_TRY(ctx, cudaGetLastError());
+      }
       ds->n_batched += (uint32_t)batch.size();
       ds->bytes_local += batch_bytes;
       batch.clear();
