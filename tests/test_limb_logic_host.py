@@ -21,6 +21,23 @@ def emul(tmp_path_factory):
     return C.CDLL(out)
 
 
+@pytest.fixture(scope="module")
+def emul_ubsan(tmp_path_factory):
+    """the same library built with -fsanitize=undefined -fno-sanitize-recover: any undefined behaviour in the shared header
+    logic (over-wide shifts, misaligned or out-of-range accesses the compiler can see, signed overflow) aborts the test run.
+    compute-sanitizer is closed on the GPU pool, so this is the sanitizer coverage the limb logic gets."""
+    out = str(tmp_path_factory.mktemp("emul_ubsan") / "liblimb_ubsan.so")
+    src = os.path.join(ROOT, "tests", "host_emul", "limb_logic.cpp")
+    res = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-shared", "-fPIC",
+                          "-I" + os.path.join(ROOT, "tests", "host_emul"), "-o", out, src], capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("this g++ cannot build with -fsanitize=undefined: " + res.stderr[-200:])
+    try:
+        return C.CDLL(out)
+    except OSError as e:
+        pytest.skip("the UBSan runtime is not loadable: " + str(e))
+
+
 def f2b(x): return int(x).to_bytes(32, "little")
 def b2f(b): return int.from_bytes(b, "little")
 
@@ -146,3 +163,26 @@ def test_chunk_reader_and_sponge_padding(emul, orc):
         for rate in (1, 2):
             emul.emul_sponge(b"".join(f2b(x) for x in xs), n, rate, out)
             assert b2f(out.raw) == orc.sponge(xs, rate)
+
+
+def test_limb_logic_under_ubsan(emul_ubsan, orc):
+    """permutation, byte hashing on both loaders, sponge and compression through the UBSan build: results equal the oracle
+    and nothing undefined is executed on the way"""
+    rnd = random.Random(31)
+    out = C.create_string_buffer(96)
+    for s in [(0, 1, 2), (R - 1, R - 1, R - 1)] + [tuple(rnd.randrange(R) for _ in range(3)) for _ in range(10)]:
+        emul_ubsan.emul_permutation(b"".join(f2b(x) for x in s), out)
+        assert tuple(b2f(out.raw[i:i + 32]) for i in (0, 32, 64)) == orc.permutation(s)
+    o32 = C.create_string_buffer(32)
+    for n in list(range(0, 70)) + [2047, 2048, 4096]:
+        d = bytes(rnd.randrange(256) for _ in range(n))
+        emul_ubsan.emul_hash_bytes(d, n, o32)
+        assert b2f(o32.raw) == orc.hash_bytes(d), n
+        if n % 4 == 0 and n:
+            buf = C.create_string_buffer(d, n)
+            emul_ubsan.emul_hash_cell_aligned(buf, n, o32)
+            assert b2f(o32.raw) == orc.hash_bytes(d), n
+    for k in range(4):
+        x, y = rnd.randrange(R), rnd.randrange(R)
+        emul_ubsan.emul_compress(f2b(x), f2b(y), k, o32)
+        assert b2f(o32.raw) == orc.compress(x, y, k)
