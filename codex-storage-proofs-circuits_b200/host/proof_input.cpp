@@ -135,7 +135,7 @@ std::vector<F> elements(const std::vector<uint8_t>& bytes) {   // 31-byte LE chu
   for (size_t k = 0; k < n; ++k) {
     const size_t off = 31 * k;
     const size_t m = std::min<size_t>(31, bytes.size() - off);
-    std::memcpy(out[k].data(), bytes.data() + off, m);
+    if (m) std::memcpy(out[k].data(), bytes.data() + off, m);      // an empty input has no data pointer to copy from
     if (m < 31) out[k][m] = 0x01;
   }
   return out;

@@ -46,6 +46,39 @@ int main() {
   CHECK(extractLowBits(felt(0xabcdef), 8) == 0xef && extractLowBits(felt(0xabcdef), 64) == 0xabcdef);
   CHECK(parametricSlotSeed(12345, 3) == 12345 + 72 + 3003);
 
+  // more pure host logic: decimal rendering (types/bn254.nim:29-33) at the edges, and the JSON layout on a hand-made input
+  {
+    F big{};
+    for (int i = 0; i < 32; ++i) big[i] = 0xff;
+    CHECK(toDecimalF(big) == "115792089237316195423570985008687907853269984665640564039457584007913129639935");   // 2^256 - 1
+    F p10{};                                          // 10^18 = 0x0de0b6b3a7640000
+    const uint64_t v = 1000000000000000000ull;
+    std::memcpy(p10.data(), &v, 8);
+    CHECK(toDecimalF(p10) == "1000000000000000000");
+    CHECK(toDecimalF(intToBN254(-1)) == "21888242871839275222246405745257275088548364400416034343698204186575808495616");   // r - 1
+    SlotProofInput prf;
+    prf.dataSetRoot = felt(7);
+    prf.entropy = felt(8);
+    prf.nCells = 64;
+    prf.nSlots = 3;
+    prf.slotIndex = 2;
+    prf.slotRoot = felt(9);
+    prf.slotProof.merklePath = {felt(1), felt(2)};
+    CellProofInput c;
+    c.cellData = Cell(62, 0);
+    c.merkleProof.merklePath = {felt(3)};
+    prf.proofInputs = {c};
+    const std::string js = proofInputToJson(prf);
+    CHECK(js == "{\n  \"dataSetRoot\":      \"7\"\n, \"entropy\":          \"8\"\n, \"nCellsPerSlot\":    64\n, \"nSlotsPerDataSet\": 3\n, \"slotIndex\":        2\n"
+                ", \"slotRoot\":         \"9\"\n, \"slotProof\":\n    [ \"1\"\n    , \"2\"\n    ]\n, \"cellData\":\n    [ [ \"0\"\n      , \"0\"\n      , \"1\"\n      ]\n    ]\n"
+                ", \"merklePaths\":\n    [ [ \"3\"\n      ]\n    ]\n}\n");
+    if (js.size() < 10) std::printf("%s", js.c_str());
+  }
+#ifdef CDX_TEST_PURE_ONLY
+  std::printf(failures ? "%d FAILURES\n" : "host mirror (pure logic): all checks passed\n", failures);
+  return failures ? 1 : 0;
+#endif
+
   // ---- over the GPU backend ----
   Backend be(0);
   HashConfig h;
