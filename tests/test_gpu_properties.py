@@ -574,3 +574,45 @@ def test_cell_sponge_launch_boundary(pkg, ctx, torch_mod):
         with small.slot_commit_host(host, cell, block) as c, ctx.slot_commit_host(host, cell, block) as e:
             assert c.root == e.root
     small.close()
+
+
+def test_guard_bands_around_caller_buffers(ctx, torch_mod):
+    """device-side memory safety without compute-sanitizer (closed on this pool): every entry point that writes into a
+    caller's device buffer is run with ragged sizes (partial warps, partial CTAs, sizes around the launch-width switches)
+    between two guard bands, which must come back untouched"""
+    torch = torch_mod
+    G = 4096
+
+    def guarded(n_bytes):
+        buf = torch.full((n_bytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf.data_ptr() + G
+
+    def intact(buf, n_bytes):
+        torch.cuda.synchronize()
+        return bool((buf[:G] == 0xA5).all()) and bool((buf[G + n_bytes:] == 0xA5).all())
+
+    for cell in (2048, 64, 100):                                         # TMA kernel (two geometries) and the plain-load kernel
+        for n_cells in (1, 31, 33, 255, 257, 4735, 4737, 9473, 20001):
+            src = synthetic(ctx, torch, (n_cells * cell + 7) // 8 * 8, seed=n_cells)
+            out, p = guarded(32 * n_cells)
+            ctx.hash_cells_dev(src.data_ptr(), n_cells, cell, p)
+            assert intact(out, 32 * n_cells), (cell, n_cells)
+    for n in (1, 33, 1000, 37889):
+        src = synthetic(ctx, torch, 96 * n, seed=n)
+        out, p = guarded(96 * n)
+        ctx.permutation_batch_dev(src.data_ptr(), p, n)
+        assert intact(out, 96 * n), n
+    for n_cells, cell in ((1, 2048), (37, 2048), (300, 64), (129, 100)):
+        out, p = guarded(n_cells * cell)
+        ctx.fake_cells_dev(99, 5, n_cells, cell, p)
+        assert intact(out, n_cells * cell), (n_cells, cell)
+    for n_bytes in (8, 4096 + 8, 1 << 20):
+        out, p = guarded(n_bytes)
+        ctx.fill_synthetic_dev(3, 17, n_bytes, p)
+        assert intact(out, n_bytes), n_bytes
+    d = synthetic(ctx, torch, 100 * 65536)
+    with ctx.slot_commit_range_dev(d.data_ptr(), 100 * 65536, 2048, 65536, 0, 100, 2) as sh:      # 25 level-2 nodes
+        _, cnt, _ = sh.subtree_roots()
+        out, p = guarded(32 * cnt)
+        sh.subtree_roots_copy_dev(p)
+        assert cnt == 25 and intact(out, 32 * cnt)
