@@ -63,6 +63,7 @@ SYMBOLS = {
     "cdx_fake_cells_dev": (_int, [_vp, _u64, _u64, _sz, _sz, _vp, _vp]),
     "cdx_fill_synthetic_dev": (_int, [_vp, _u64, _u64, _sz, _vp, _vp]),
     "cdx_probe_imad_rate": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cdx_debug_guard_selftest": (_int, [_vp]),
     "cdx_merkle_root_bytes_host": (_int, [_vp, _vp, _sz, _vp]),
     "cdx_slots_commit_batch_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp, _vp]),
     "cdx_slots_commit_batch_host": (_int, [_vp, _vp, _vp, _sz, _sz, _sz, _vp]),

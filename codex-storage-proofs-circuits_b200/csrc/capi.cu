@@ -15,8 +15,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <new>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.cuh"
@@ -77,6 +79,11 @@ struct cdx_slot {
   std::vector<uint8_t*> forest, low, top;             // per-level pointers (low[0] aliases forest[block_depth])
   std::vector<uint64_t> low_first, low_count, width;  // width[l] = global width of slot level l
 };
+
+namespace {   // device allocations between optional guard bands (defined below, CODEX_COMMIT_GUARD)
+bool guard_enabled();
+void dev_free(void* p, cudaStream_t st);
+}  // namespace
 
 static int fail(cdx_ctx* ctx, int status, const char* fmt, ...) {
   if (ctx) {
@@ -199,7 +206,10 @@ extern "C" void cdx_ctx_destroy(cdx_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (int i = 0; i < CDX_MAX_STAGE; ++i) {
-    if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    if (ctx->d_stage[i]) {
+      if (guard_enabled()) dev_free(ctx->d_stage[i], ctx->stream);
+      else cudaFree(ctx->d_stage[i]);
+    }
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
   }
@@ -222,6 +232,81 @@ extern "C" const char* cdx_last_error(const cdx_ctx* ctx) { return ctx ? ctx->er
 extern "C" uint64_t cdx_launch_count(const cdx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* cdx_ctx_stream(const cdx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+// ---- device allocations, optionally between guard bands -------------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool this library is developed on.  CODEX_COMMIT_GUARD=1 is the
+// substitute for out-of-bounds WRITES: every device allocation of the library (tree layers, staging tiles, scoped
+// buffers) gets a 4 KiB band of 0xA5 on either side, and freeing it first reads the bands back; a damaged band is
+// reported on stderr and aborts the process.  A debug mode: the check synchronises the stream at every free.
+namespace {
+constexpr size_t kGuardBytes = 4096;
+struct GuardInfo {
+  size_t bytes;
+  bool stream_ordered;
+};
+bool guard_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("CODEX_COMMIT_GUARD");
+    return v && v[0] == '1';
+  }();
+  return on;
+}
+std::mutex g_guard_mutex;
+std::unordered_map<void*, GuardInfo> g_guard_live;
+
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t st, bool stream_ordered = true) {
+  if (bytes == 0) bytes = 1;
+  if (!guard_enabled()) return stream_ordered ? cudaMallocAsync(p, bytes, st) : cudaMalloc(p, bytes);
+  uint8_t* raw = nullptr;
+  const size_t padded = (bytes + 255) / 256 * 256;       // the far band starts 256-byte aligned as well
+  cudaError_t e = stream_ordered ? cudaMallocAsync((void**)&raw, padded + 2 * kGuardBytes, st) : cudaMalloc((void**)&raw, padded + 2 * kGuardBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(raw, 0xA5, kGuardBytes, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(raw + kGuardBytes + bytes, 0xA5, padded - bytes + kGuardBytes, st);
+  if (e != cudaSuccess) return e;
+  *p = raw + kGuardBytes;
+  std::lock_guard<std::mutex> lock(g_guard_mutex);
+  g_guard_live[*p] = GuardInfo{bytes, stream_ordered};
+  return cudaSuccess;
+}
+
+void dev_free(void* p, cudaStream_t st) {
+  if (!p) return;
+  if (!guard_enabled()) {
+    cudaFreeAsync(p, st);
+    return;
+  }
+  GuardInfo info{0, true};
+  {
+    std::lock_guard<std::mutex> lock(g_guard_mutex);
+    auto it = g_guard_live.find(p);
+    if (it == g_guard_live.end()) {
+      fprintf(stderr, "CODEX_COMMIT_GUARD: free of an unknown device pointer %p\n", p);
+      abort();
+    }
+    info = it->second;
+    g_guard_live.erase(it);
+  }
+  uint8_t* raw = (uint8_t*)p - kGuardBytes;
+  const size_t padded = (info.bytes + 255) / 256 * 256, tail = padded - info.bytes + kGuardBytes;
+  std::vector<uint8_t> head(kGuardBytes), far(tail);
+  cudaMemcpyAsync(head.data(), raw, kGuardBytes, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(far.data(), raw + kGuardBytes + info.bytes, tail, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) cudaGetLastError();
+  for (size_t i = 0; i < kGuardBytes; ++i)
+    if (head[i] != 0xA5) {
+      fprintf(stderr, "CODEX_COMMIT_GUARD: %zu-byte allocation %p: write %zu bytes BEFORE its start\n", info.bytes, p, kGuardBytes - i);
+      abort();
+    }
+  for (size_t i = 0; i < tail; ++i)
+    if (far[i] != 0xA5) {
+      fprintf(stderr, "CODEX_COMMIT_GUARD: %zu-byte allocation %p: write %zu bytes PAST its end\n", info.bytes, p, i);
+      abort();
+    }
+  if (info.stream_ordered) cudaFreeAsync(raw, st);
+  else cudaFree(raw);
+}
+}  // namespace
+
 // Scoped device buffer for the *_host entry points.  Stream-ordered allocation from the device's default memory
 // pool (release threshold raised to "never" in cdx_ctx_create): cudaMalloc/cudaFree cost tens to hundreds of
 // milliseconds for tree-sized buffers on this platform and serialise the device, cudaMallocAsync/cudaFreeAsync
@@ -230,11 +315,11 @@ struct DevBuf {
   void* p = nullptr;
   cudaStream_t st = nullptr;
   ~DevBuf() {
-    if (p) cudaFreeAsync(p, st);
+    if (p) dev_free(p, st);
   }
   cudaError_t alloc(size_t bytes, cudaStream_t stream) {
     st = stream;
-    return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    return dev_alloc(&p, bytes, stream);
   }
   uint8_t* u8() const { return static_cast<uint8_t*>(p); }
 };
@@ -496,9 +581,9 @@ static uint32_t log2_u64(uint64_t x) {
 extern "C" void cdx_slot_free(cdx_slot* s) {
   if (!s) return;
   if (s->ctx) cudaSetDevice(s->ctx->device);
-  if (s->d_forest) cudaFreeAsync(s->d_forest, s->stream);   // ordered after everything queued on the slot's stream
-  if (s->d_low) cudaFreeAsync(s->d_low, s->stream);
-  if (s->d_top) cudaFreeAsync(s->d_top, s->stream);
+  if (s->d_forest) dev_free(s->d_forest, s->stream);   // ordered after everything queued on the slot's stream
+  if (s->d_low) dev_free(s->d_low, s->stream);
+  if (s->d_top) dev_free(s->d_top, s->stream);
   delete s;
 }
 
@@ -576,8 +661,8 @@ static int slot_alloc(cdx_ctx* ctx, uint64_t n_local_blocks, size_t cell_size, s
     l_off.push_back(low_nodes);
     low_nodes += s->low_count[l];
   }
-  cudaError_t e = forest_nodes ? cudaMallocAsync((void**)&s->d_forest, 32 * forest_nodes, st) : cudaSuccess;
-  if (e == cudaSuccess && low_nodes) e = cudaMallocAsync((void**)&s->d_low, 32 * low_nodes, st);
+  cudaError_t e = forest_nodes ? dev_alloc((void**)&s->d_forest, 32 * forest_nodes, st) : cudaSuccess;
+  if (e == cudaSuccess && low_nodes) e = dev_alloc((void**)&s->d_low, 32 * low_nodes, st);
   if (e != cudaSuccess) {
     cdx_slot_free(s);
     return fail(ctx, CDX_ERR_ALLOC, "cudaMalloc of %zu tree nodes failed: %s", forest_nodes + low_nodes, cudaGetErrorString(e));
@@ -620,10 +705,10 @@ static int build_top(cdx_slot* s, const uint8_t* d_level_nodes, bool alias) {
     if (!(alias && l == T)) nodes += s->width[l];
   }
   if (s->d_top) {
-    cudaFreeAsync(s->d_top, s->stream);
+    dev_free(s->d_top, s->stream);
     s->d_top = nullptr;
   }
-  if (nodes) CU_TRY(ctx, cudaMallocAsync((void**)&s->d_top, 32 * nodes, s->stream));
+  if (nodes) CU_TRY(ctx, dev_alloc((void**)&s->d_top, 32 * nodes, s->stream));
   s->top.assign(s->slot_depth + 1, nullptr);
   for (uint32_t l = T; l <= s->slot_depth; ++l) s->top[l] = s->d_top + 32 * off[l - T];
   if (alias) {
@@ -681,18 +766,23 @@ extern "C" int cdx_slot_commit_dev(cdx_ctx* ctx, const void* d_data, size_t n_by
   return CDX_OK;
 }
 
+static void stage_free(cdx_ctx* ctx, void* p) {
+  if (guard_enabled()) dev_free(p, ctx->stream);
+  else cudaFree(p);
+}
+
 static int ensure_stage(cdx_ctx* ctx, size_t bytes, int count = 2) {
   if (ctx->stage_bytes >= bytes && ctx->stage_count >= count) return CDX_OK;
   const size_t want_bytes = bytes > ctx->stage_bytes ? bytes : ctx->stage_bytes;
   const int want_count = count > ctx->stage_count ? count : ctx->stage_count;
   CU_TRY(ctx, cudaDeviceSynchronize());                       // earlier calls may still be reading the old tiles
   for (int i = 0; i < CDX_MAX_STAGE; ++i) {
-    if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    if (ctx->d_stage[i]) stage_free(ctx, ctx->d_stage[i]);
     ctx->d_stage[i] = nullptr;
   }
   ctx->stage_bytes = 0;
   ctx->stage_count = 0;
-  for (int i = 0; i < want_count; ++i) CU_TRY(ctx, cudaMalloc(&ctx->d_stage[i], want_bytes));
+  for (int i = 0; i < want_count; ++i) CU_TRY(ctx, dev_alloc(&ctx->d_stage[i], want_bytes, ctx->stream, false));
   ctx->stage_bytes = want_bytes;
   ctx->stage_count = want_count;
   return CDX_OK;
@@ -1116,7 +1206,7 @@ extern "C" int cdx_slot_import(cdx_ctx* ctx, const uint8_t* image, size_t image_
     const uint8_t* p = image + sizeof h;
     CU_TRY(ctx, cudaMemcpyAsync(s->d_forest, p, 32 * h.forest_nodes, cudaMemcpyHostToDevice, s->stream));
     p += 32 * h.forest_nodes;
-    if (top_nodes) CU_TRY(ctx, cudaMallocAsync((void**)&s->d_top, 32 * top_nodes, s->stream));
+    if (top_nodes) CU_TRY(ctx, dev_alloc((void**)&s->d_top, 32 * top_nodes, s->stream));
     s->top.assign(s->slot_depth + 1, nullptr);
     s->top[0] = s->low[0];
     size_t off = 0;
@@ -1382,6 +1472,18 @@ extern "C" int cdx_probe_imad_rate(cdx_ctx* ctx, int kind, double* ops_per_secon
   *ops_per_second = ops / (best * 1e-3);
   if (elapsed_ms) *elapsed_ms = best;
   return CDX_OK;
+}
+
+extern "C" int cdx_debug_guard_selftest(cdx_ctx* ctx) {
+  if (!ctx) return CDX_ERR_ARG;
+  if (!guard_enabled()) return fail(ctx, CDX_ERR_STATE, "CODEX_COMMIT_GUARD=1 is not set: nothing to test");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  {
+    DevBuf d;
+    CU_TRY(ctx, d.alloc(100, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d.u8() + 100, 0, 1, ctx->stream));   // one byte past the end, on purpose
+  }                                                                  // ~DevBuf -> dev_free -> abort()
+  return fail(ctx, CDX_ERR_STATE, "the guard band did not catch a deliberate overrun");
 }
 
 #include "capi_multi.cuh"

@@ -350,6 +350,13 @@ int cdx_fill_synthetic_dev(cdx_ctx* ctx, uint64_t seed, uint64_t first_word, siz
  * multiplicand), 1 = IMAD.WIDE.U32.X carry chains as in the Montgomery rows, 2 = 32-bit IMAD. */
 int cdx_probe_imad_rate(cdx_ctx* ctx, int kind, double* ops_per_second, double* elapsed_ms);
 
+/* Debug aid.  With CODEX_COMMIT_GUARD=1 in the environment every device allocation of the library sits between two 4 KiB
+ * guard bands that are verified when it is freed; a damaged band aborts the process with a message (the pool this was
+ * developed on offers no compute-sanitizer).  This call proves the mechanism: it allocates a scoped buffer, writes one
+ * byte past its end on purpose and frees it -- in guard mode the process aborts, otherwise it returns CDX_ERR_STATE
+ * without touching anything. */
+int cdx_debug_guard_selftest(cdx_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

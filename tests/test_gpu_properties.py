@@ -616,3 +616,30 @@ def test_guard_bands_around_caller_buffers(ctx, torch_mod):
         out, p = guarded(32 * cnt)
         sh.subtree_roots_copy_dev(p)
         assert cnt == 25 and intact(out, 32 * cnt)
+
+
+def test_library_allocations_between_guard_bands():
+    """CODEX_COMMIT_GUARD=1 puts 4 KiB guard bands around EVERY device allocation the library makes (tree layers, top
+    trees, staging tiles, scoped buffers) and aborts the process if a band is damaged when the allocation is freed: a
+    representative part of the GPU suite -- ragged slots, every cell path, batches, datasets with all source kinds, the
+    sharded entry points, export/import, the geometry fuzz -- must pass unchanged in that mode"""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    select = ("config1_slot or ragged_block_counts or other_cell_and_block_sizes or every_cell_path or export_import or prove_batch_many "
+              "or batched_small_slots or dataset_commit_small or dataset_commit_mixed or sharded_entry_points or sharded_commit_equals "
+              "or fuzz_geometries or commit_file_vs_oracle or launch_boundary")
+    env = dict(os.environ, CODEX_COMMIT_GUARD="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-x", "-q", "-k", select],
+                         capture_output=True, text=True, env=env, timeout=1500, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "CODEX_COMMIT_GUARD" not in res.stderr
+    assert " passed" in res.stdout
+    # and the mechanism itself: a deliberate one-byte overrun must abort the process in guard mode, and only then
+    probe = ("import importlib, sys; sys.path.insert(0, %r); p = importlib.import_module('codex-storage-proofs-circuits_b200'); "
+             "c = p.Context(0); print('rc', c.lib.cdx_debug_guard_selftest(c.h))" % ROOT)
+    bad = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, env=env, timeout=300)
+    assert bad.returncode != 0 and "PAST its end" in bad.stderr, bad.stdout + bad.stderr
+    off = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, env=dict(os.environ, CODEX_COMMIT_GUARD="0"), timeout=300)
+    assert off.returncode == 0 and "rc -7" in off.stdout, off.stdout + off.stderr
