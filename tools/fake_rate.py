@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Rate of the reference's fake-data generator on the device (k_fake_cells) and of a commit that generates its bytes tile by
+tile (cdx_slot_commit_fake) against the same slot committed resident; 1 GiB.  Not part of bench.py."""
 import importlib, sys, time, os
 sys.path.insert(0, os.getcwd())
 import torch
